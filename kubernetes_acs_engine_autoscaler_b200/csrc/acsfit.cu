@@ -1,0 +1,1275 @@
+// acsfit.cu -- C ABI (include/acsfit.h) over the sm_100a kernels in acsfit_kernels.cuh.
+// Host orchestration only: argument checks, scratch arena, launches, the per-pool loop of
+// fulfill_pending.  There is no CPU implementation of any computation in this file: without a
+// CUDA device acsfit_ctx_create fails and nothing else can be called.
+#include "../../include/acsfit.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "acsfit_kernels.cuh"
+
+using namespace acsfit;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct acsfit_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int min_stages = 0;       // 0 = 2 x SMs
+    int watchdog_ms = 20000;
+    char err[512] = {0};
+    // grow-only device arena, bump-allocated per API call
+    unsigned char *arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    // device copies of the host-entry buffers (grow-only)
+    unsigned char *hbuf = nullptr;
+    size_t hbuf_cap = 0, hbuf_off = 0;
+    uint64_t launches = 0;
+    // pipeline statistics of the last first-fit / bin-pack call
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    uint64_t last_decisions = 0;
+    int last_stages = 0, last_tiles = 0;
+};
+
+static acsfit_status fail(acsfit_ctx *ctx, acsfit_status code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(ctx, ACSFIT_E_CUDA, "%s failed: %s (%s:%d)", #expr,                      \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+    } while (0)
+
+#define TRY(expr)                                \
+    do {                                         \
+        acsfit_status s__ = (expr);              \
+        if (s__ != ACSFIT_OK) return s__;        \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static acsfit_status arena_reserve(acsfit_ctx *ctx, size_t bytes, cudaStream_t st)
+{
+    if (bytes <= ctx->arena_cap) return ACSFIT_OK;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ctx->arena) CUDA_TRY(cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_cap = 0;
+    size_t cap = align_up(bytes + bytes / 4, 1 << 20);
+    CUDA_TRY(cudaMalloc(&ctx->arena, cap));
+    ctx->arena_cap = cap;
+    return ACSFIT_OK;
+}
+
+template <typename T>
+static T *arena_take(acsfit_ctx *ctx, size_t count)
+{
+    size_t off = align_up(ctx->arena_off, 256);
+    size_t bytes = sizeof(T) * std::max<size_t>(count, 1);
+    if (off + bytes > ctx->arena_cap) return nullptr;  // callers reserve an upper bound first
+    ctx->arena_off = off + bytes;
+    return reinterpret_cast<T *>(ctx->arena + off);
+}
+
+#define TAKE(var, T, count)                                                                 \
+    T *var = arena_take<T>(ctx, (count));                                                   \
+    if (!var) return fail(ctx, ACSFIT_E_NOMEM, "scratch arena too small for %s", #var)
+
+static inline int grid_for(const acsfit_ctx *ctx, int64_t n, int block)
+{
+    int64_t g = (n + block - 1) / block;
+    int64_t cap = (int64_t)ctx->num_sms * 8;
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+// ---------------------------------------------------------------------------------------------
+// utility kernels (ordered compaction, reductions, scatter)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kCompactBlock = 256;
+constexpr int kCompactItems = 8;  // per thread, consecutive
+constexpr int kCompactChunk = kCompactBlock * kCompactItems;
+
+struct FlagPred {
+    const uint8_t *flag;
+    __device__ bool operator()(int64_t i) const { return flag[i] != 0; }
+};
+struct BitPred {
+    const uint32_t *bits;
+    __device__ bool operator()(int64_t i) const { return (bits[i >> 5] >> (i & 31)) & 1u; }
+};
+
+template <typename Pred>
+__global__ void compact_count_kernel(Pred pred, int64_t n, int *block_counts)
+{
+    __shared__ int wsum[kCompactBlock / 32];
+    const int64_t base = (int64_t)blockIdx.x * kCompactChunk + (int64_t)threadIdx.x * kCompactItems;
+    int c = 0;
+    for (int i = 0; i < kCompactItems; ++i) c += (base + i < n && pred(base + i)) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kCompactBlock / 32; ++w) t += wsum[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of block_counts (single block), total -> *out_total
+__global__ void compact_scan_kernel(int *block_counts, int nblocks, int64_t *out_total)
+{
+    __shared__ long long carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? block_counts[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            wsum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const long long warp_off = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+        const long long incl = carry + warp_off + x;
+        if (i < nblocks) block_counts[i] = (int)(incl - v);  // exclusive (fits: total <= 2^31)
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_total = carry;
+}
+
+// scatter: out[offset + rank] = map ? map[i] : i   for every i with pred(i), order preserved
+template <typename Pred>
+__global__ void compact_scatter_kernel(Pred pred, int64_t n, const int *block_offsets,
+                                       const int32_t *map, int32_t *out)
+{
+    __shared__ int wsum[kCompactBlock / 32];
+    const int64_t base = (int64_t)blockIdx.x * kCompactChunk + (int64_t)threadIdx.x * kCompactItems;
+    bool f[kCompactItems];
+    int c = 0;
+    for (int i = 0; i < kCompactItems; ++i) {
+        f[i] = base + i < n && pred(base + i);
+        c += f[i] ? 1 : 0;
+    }
+    int x = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int warp_off = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) warp_off += wsum[w];
+    int pos = block_offsets[blockIdx.x] + warp_off + x - c;
+    for (int i = 0; i < kCompactItems; ++i)
+        if (f[i]) out[pos++] = map ? map[base + i] : (int32_t)(base + i);
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// alive bits: all ones for entries < n
+__global__ void fill_alive_kernel(uint32_t *w, int64_t n)
+{
+    const int64_t nw = (n + 31) / 32;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nw; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rem = n - i * 32;
+        w[i] = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+    }
+}
+
+// credited can_fit calls from a placement vector: sum(placed >= 0 ? placed + 1 : N)
+__global__ void decisions_kernel(const int32_t *placed, int64_t P, int64_t N, unsigned long long *out)
+{
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = placed[i];
+        c += v >= 0 ? (unsigned long long)v + 1ull : (unsigned long long)N;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// after a bins pass: cur_bin[pod] = placed[j] for the placed list entries; also max bin
+__global__ void scatter_bins_kernel(const int32_t *list, const int32_t *placed, int64_t M,
+                                    int32_t *cur_bin, int32_t *bin_of, int *max_bin)
+{
+    int m = -1;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = placed[j];
+        if (b >= 0) {
+            const int32_t pod = list[j];
+            cur_bin[pod] = b;
+            bin_of[pod] = b;
+            m = max(m, b);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(max_bin, m);
+}
+
+// scaler.py:172-175: pods of the first `take` bins become accounted
+__global__ void account_kernel(const int32_t *cur_bin, int64_t P, int32_t take, int32_t pool,
+                               int32_t *acc_pool, unsigned long long *count)
+{
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = cur_bin[i];
+        if (b >= 0 && b < take) {
+            acc_pool[i] = pool;
+            ++c;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+// domain check: requests must be >= 0 and not NaN; flag[0] |= 1 otherwise
+__global__ void domain_kernel(const double *v, int64_t n, int *flag)
+{
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        bad = bad || !(v[i] >= 0.0);
+    if (bad) atomicOr(flag, 1);
+}
+
+// K6: Scaler.get_node_state (scaler.py:61-114), one thread per node, S thresholds at once
+__global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ run_idx,
+                                   const double *__restrict__ req_run, const uint8_t *__restrict__ flags_run,
+                                   const double *__restrict__ cap_type, const int32_t *__restrict__ node_type,
+                                   const uint8_t *__restrict__ node_flags, const int64_t *__restrict__ node_age,
+                                   int64_t N, int D, int any_pending,
+                                   const int64_t *__restrict__ idle_threshold, int S,
+                                   uint8_t *__restrict__ out_state)
+{
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        double util[kMaxDims];
+        for (int d = 0; d < D; ++d) util[d] = 0.0;
+        bool busy = false, undrainable = false;
+        const int64_t k1 = row_ptr[n + 1];
+        for (int64_t k = row_ptr[n]; k < k1; ++k) {
+            const int32_t j = run_idx[k];
+            const uint8_t f = flags_run[j];
+            undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
+            if (f & ACSFIT_PODF_BUSY) {
+                busy = true;
+                const double *r = req_run + (size_t)j * D;
+                for (int d = 0; d < D; ++d) util[d] = __dadd_rn(util[d], r[d]);  // ordered sum
+            }
+        }
+        const double *cap = cap_type + (size_t)node_type[n] * D;
+        bool under = true;
+        for (int d = 0; d < D; ++d) {
+            // (UTIL_THRESHOLD * capacity - utilization).possible: multiply THEN subtract, no FMA
+            const double left = __dsub_rn(__dmul_rn(cap[d], 0.3), util[d]);
+            under = under && (left >= 0.0);
+        }
+        const bool unsched = node_flags[n] & ACSFIT_NODEF_UNSCHEDULABLE;
+        const int64_t age = node_age[n];
+        for (int s = 0; s < S; ++s) {
+            uint8_t st;
+            if (busy && !under) st = unsched ? ACSFIT_ST_BUSY_UNSCHEDULABLE : ACSFIT_ST_BUSY;
+            else if (any_pending && !unsched) st = ACSFIT_ST_POD_PENDING;
+            else if (age <= idle_threshold[s] && !unsched) st = ACSFIT_ST_GRACE_PERIOD;
+            else if (under && (busy || !unsched))
+                st = undrainable ? ACSFIT_ST_UNDER_UTILIZED_UNDRAINABLE : ACSFIT_ST_UNDER_UTILIZED_DRAINABLE;
+            else st = unsched ? ACSFIT_ST_IDLE_UNSCHEDULABLE : ACSFIT_ST_IDLE_SCHEDULABLE;
+            out_state[(size_t)s * N + n] = st;
+        }
+    }
+}
+
+// maintain actions ------------------------------------------------------------------------
+constexpr int kMaintBlock = 256;
+constexpr int kMaintRounds = 16;                       // nodes per block = 256 * 16
+constexpr int kMaintChunk = kMaintBlock * kMaintRounds;
+
+// phase 1 (only when the budget decrements, i.e. not dry_run): per-chunk, per-pool count of
+// UNDER_UTILIZED_DRAINABLE nodes of scalable pools
+__global__ void maintain_count_kernel(const uint8_t *state, const int32_t *node_pool, int64_t N,
+                                      const uint8_t *pool_scalable, int T, int *counts /*[chunks][T]*/)
+{
+    extern __shared__ int hist[];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) hist[t] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kMaintChunk;
+    for (int r = 0; r < kMaintRounds; ++r) {
+        const int64_t n = base + (int64_t)r * kMaintBlock + threadIdx.x;
+        if (n < N) {
+            const int t = node_pool[n];
+            if (t >= 0 && t < T && pool_scalable[t] && state[n] == ACSFIT_ST_UNDER_UTILIZED_DRAINABLE)
+                atomicAdd(&hist[t], 1);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) counts[(size_t)blockIdx.x * T + t] = hist[t];
+}
+
+// phase 2: exclusive scan over chunks for every pool (one thread per pool)
+__global__ void maintain_scan_kernel(int *counts, int chunks, int T)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    long long run = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const int v = counts[(size_t)c * T + t];
+        counts[(size_t)c * T + t] = (int)run;
+        run += v;
+    }
+}
+
+// phase 3: SPARE_AGENT substitution + action table, in node order inside each pool
+__global__ void maintain_apply_kernel(uint8_t *state, const int32_t *node_pool, int64_t N,
+                                      const long long *budget0, const uint8_t *pool_scalable, int T,
+                                      int dry_run, const int *chunk_rank /*[chunks][T] or null*/,
+                                      uint8_t *action)
+{
+    extern __shared__ int running[];  // per pool: UUD nodes seen so far in this chunk
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+        running[t] = chunk_rank ? chunk_rank[(size_t)blockIdx.x * T + t] : 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kMaintChunk;
+    for (int r = 0; r < kMaintRounds; ++r) {
+        const int64_t n = base + (int64_t)r * kMaintBlock + threadIdx.x;
+        const bool in = n < N;
+        int t = in ? node_pool[n] : -1;
+        const bool scal = in && t >= 0 && t < T && pool_scalable[t];
+        uint8_t st = in ? state[n] : 0;
+        const bool uud = scal && st == ACSFIT_ST_UNDER_UTILIZED_DRAINABLE;
+        int rank = 0;
+        if (!dry_run) {
+            // rank of this node among the UUD nodes of its pool, in node order: warps take turns
+            for (int w = 0; w < kMaintBlock / 32; ++w) {
+                if (warp == w) {
+                    const unsigned um = __ballot_sync(0xFFFFFFFFu, uud);
+                    if (uud) {
+                        const unsigned same = __match_any_sync(um, t);
+                        const int seen = running[t];
+                        __syncwarp(um);  // everyone has read the counter before a leader bumps it
+                        rank = seen + __popc(same & ((1u << lane) - 1u));
+                        if ((int)(__ffs(same) - 1) == lane) running[t] = seen + __popc(same);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (!in) continue;
+        uint8_t act = ACSFIT_ACT_NONE;
+        if (!scal) {
+            st = ACSFIT_ST_NOT_EVALUATED;
+        } else {
+            if (uud) {
+                const long long b0 = budget0[t];
+                // engine_scaler.py:142-144: spare when the budget is exactly 0 at this node's turn.
+                // dry run: the budget never moves.  otherwise it drops by one per drained node and
+                // stays at 0 once it got there (a negative start never reaches 0).
+                const bool spare = dry_run ? (b0 == 0) : (b0 >= 0 && (long long)rank >= b0);
+                if (spare) st = ACSFIT_ST_SPARE_AGENT;
+            }
+            switch (st) {
+            case ACSFIT_ST_UNDER_UTILIZED_DRAINABLE: act = ACSFIT_ACT_CORDON_DRAIN; break;
+            case ACSFIT_ST_IDLE_SCHEDULABLE: act = ACSFIT_ACT_CORDON; break;
+            case ACSFIT_ST_BUSY_UNSCHEDULABLE: act = ACSFIT_ACT_UNCORDON; break;
+            case ACSFIT_ST_IDLE_UNSCHEDULABLE: act = ACSFIT_ACT_SCALE_IN; break;
+            default: break;
+            }
+        }
+        state[n] = st;
+        action[n] = act;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// ABI: context
+// ---------------------------------------------------------------------------------------------
+extern "C" int acsfit_abi_version(void) { return ACSFIT_ABI_VERSION; }
+
+extern "C" const char *acsfit_last_error(const acsfit_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
+{
+    if (!out_ctx) return ACSFIT_E_INVALID;
+    *out_ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+        return ACSFIT_E_CUDA;  // no GPU: there is no CPU fallback
+    acsfit_ctx *ctx = new (std::nothrow) acsfit_ctx();
+    if (!ctx) return ACSFIT_E_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        prop.major < 10) {
+        delete ctx;
+        return ACSFIT_E_CUDA;  // built for sm_100a only
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return ACSFIT_E_CUDA;
+    }
+    *out_ctx = ctx;
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->hbuf) cudaFree(ctx->hbuf);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_ctx_configure(acsfit_ctx *ctx, int min_stages, int watchdog_ms)
+{
+    if (!ctx || min_stages < 0 || watchdog_ms < 0) return ACSFIT_E_INVALID;
+    ctx->min_stages = min_stages;
+    if (watchdog_ms) ctx->watchdog_ms = watchdog_ms;
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_ctx_set_timing(acsfit_ctx *ctx, int enabled)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    ctx->timing = enabled != 0;
+    return ACSFIT_OK;
+}
+
+extern "C" uint64_t acsfit_launch_count(const acsfit_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" acsfit_status acsfit_last_pipeline_stats(const acsfit_ctx *ctx, double *out_ms,
+                                                    uint64_t *out_decisions, int *out_stages, int *out_tiles)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    if (out_ms) *out_ms = ctx->last_ms;
+    if (out_decisions) *out_decisions = ctx->last_decisions;
+    if (out_stages) *out_stages = ctx->last_stages;
+    if (out_tiles) *out_tiles = ctx->last_tiles;
+    return ACSFIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers shared by the entry points
+// ---------------------------------------------------------------------------------------------
+static bool pipeline_dims_ok(int D) { return D == 2 || D == 4 || D == 8 || D == 16; }
+
+static acsfit_status enter(acsfit_ctx *ctx, int D)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    if (D < 1 || D > ACSFIT_MAX_DIMS) return fail(ctx, ACSFIT_E_INVALID, "D=%d outside [1,%d]", D, ACSFIT_MAX_DIMS);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, ACSFIT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx->arena_off = 0;
+    return ACSFIT_OK;
+}
+
+static acsfit_status check_domain(acsfit_ctx *ctx, const double *v, int64_t n, int *flag_dev, cudaStream_t st,
+                                  const char *what)
+{
+    if (n <= 0) return ACSFIT_OK;
+    CUDA_TRY(cudaMemsetAsync(flag_dev, 0, sizeof(int), st));
+    domain_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(v, n, flag_dev);
+    ++ctx->launches;
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (flag) return fail(ctx, ACSFIT_E_DOMAIN, "%s contains a negative or NaN quantity", what);
+    return ACSFIT_OK;
+}
+
+// ordered compaction: out_list = [map ? map[i] : i  for i in range(n) if pred(i)]; count to host
+template <typename Pred>
+static acsfit_status compact(acsfit_ctx *ctx, Pred pred, int64_t n, const int32_t *map, int32_t *out_list,
+                             int *block_counts, int64_t *total_dev, int64_t *total_host, cudaStream_t st)
+{
+    *total_host = 0;
+    if (n <= 0) return ACSFIT_OK;
+    const int nblocks = (int)((n + kCompactChunk - 1) / kCompactChunk);
+    compact_count_kernel<<<nblocks, kCompactBlock, 0, st>>>(pred, n, block_counts);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, total_dev);
+    compact_scatter_kernel<<<nblocks, kCompactBlock, 0, st>>>(pred, n, block_counts, map, out_list);
+    ctx->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(total_host, total_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+struct StagePlan {
+    int Tn, NS, stages;
+};
+
+// cut `n_nodes` nodes into stages: the widest stage (<= 1024 nodes) that still gives at
+// least `min_stages` stages, so that every SM has a stage to run.
+static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages)
+{
+    const int want = ctx->min_stages > 0 ? ctx->min_stages : 2 * ctx->num_sms;
+    int NS = kThreads;
+    while (NS > 1 && (n_nodes + (int64_t)NS * kNodesPerThread - 1) / ((int64_t)NS * kNodesPerThread) < want) NS >>= 1;
+    StagePlan p;
+    p.NS = NS;
+    p.Tn = NS * kNodesPerThread;
+    int64_t stages = (n_nodes + p.Tn - 1) / p.Tn;
+    if (stages < 1) stages = 1;
+    if (max_stages > 0 && stages > max_stages) stages = max_stages;
+    p.stages = (int)stages;
+    return p;
+}
+
+template <int D, bool BINS>
+static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
+{
+    const size_t smem = PipelineSmem<D>::bytes(pp.Tn);
+    auto kern = firstfit_pipeline_kernel<D, BINS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<stages, kThreads, smem, st>>>(pp);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+template <bool BINS>
+static acsfit_status launch_pipeline(acsfit_ctx *ctx, int D, const PipelineParams &pp, int stages, cudaStream_t st)
+{
+    switch (D) {
+    case 2: return launch_pipeline_t<2, BINS>(ctx, pp, stages, st);
+    case 4: return launch_pipeline_t<4, BINS>(ctx, pp, stages, st);
+    case 8: return launch_pipeline_t<8, BINS>(ctx, pp, stages, st);
+    case 16: return launch_pipeline_t<16, BINS>(ctx, pp, stages, st);
+    default: return fail(ctx, ACSFIT_E_INVALID, "D=%d: the first-fit entry points need D in {2,4,8,16}", D);
+    }
+}
+
+static acsfit_status check_pipeline_status(acsfit_ctx *ctx, const int *status_dev, cudaStream_t st)
+{
+    int status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, status_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (status) return fail(ctx, ACSFIT_E_TIMEOUT, "first-fit pipeline watchdog fired after %d ms", ctx->watchdog_ms);
+    return ACSFIT_OK;
+}
+
+static void reset_stats(acsfit_ctx *ctx)
+{
+    ctx->last_ms = 0.0;
+    ctx->last_decisions = 0;
+    ctx->last_stages = ctx->last_tiles = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// first fit over nodes (implementation; scratch must already be reserved)
+// ---------------------------------------------------------------------------------------------
+static size_t first_fit_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N)
+{
+    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0);
+    return 8192 + sizeof(uint32_t) * (size_t)((P + 31) / 32) + sizeof(int) * ((size_t)plan.stages + 8);
+}
+
+static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const int32_t *pod_idx, int64_t P, int D,
+                                    const double *cap_type, const int32_t *node_type, double *used, int64_t N,
+                                    int32_t *out_placed, unsigned long long *out_decisions, cudaStream_t st)
+{
+    if (out_decisions) CUDA_TRY(cudaMemsetAsync(out_decisions, 0, sizeof(unsigned long long), st));
+    if (P == 0) return ACSFIT_OK;
+    fill_i32_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_placed, P, -1);
+    ++ctx->launches;
+    if (N == 0) {  // every pod is pending and the reference makes no can_fit call
+        CUDA_TRY(cudaGetLastError());
+        return ACSFIT_OK;
+    }
+    const StagePlan plan = plan_stages(ctx, N, 0);
+    const int64_t alive_words = (P + 31) / 32;
+    TAKE(alive, uint32_t, alive_words);
+    TAKE(sync_words, int, plan.stages + 8);
+    int *ticket = sync_words, *status = sync_words + 1, *drained = sync_words + 2, *progress = sync_words + 8;
+    CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
+    fill_alive_kernel<<<grid_for(ctx, alive_words, 256), 256, 0, st>>>(alive, P);
+    ++ctx->launches;
+
+    PipelineParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.req = req;
+    pp.pod_idx = pod_idx;
+    pp.M = P;
+    pp.alive = alive;
+    pp.placed = out_placed;
+    pp.cap_type = cap_type;
+    pp.node_type = node_type;
+    pp.used = used;
+    pp.node_lo = 0;
+    pp.node_hi = N;
+    pp.Tn = plan.Tn;
+    pp.NS = plan.NS;
+    pp.num_tiles = (int)((P + kTile - 1) / kTile);
+    pp.ticket = ticket;
+    pp.progress = progress;
+    pp.status = status;
+    pp.drained = drained;
+    pp.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    TRY(launch_pipeline<false>(ctx, D, pp, plan.stages, st));
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+    if (out_decisions) {
+        decisions_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_placed, P, N, out_decisions);
+        ++ctx->launches;
+    }
+    TRY(check_pipeline_status(ctx, status, st));
+    ctx->last_stages += plan.stages;
+    ctx->last_tiles += pp.num_tiles;
+    if (ctx->timing) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms += ms;
+        if (out_decisions) {
+            unsigned long long d = 0;
+            CUDA_TRY(cudaMemcpy(&d, out_decisions, sizeof d, cudaMemcpyDeviceToHost));
+            ctx->last_decisions += d;
+        }
+    }
+    return ACSFIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fulfill_pending (implementation; scratch must already be reserved)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxStagesPerPass = 1024;
+
+static size_t fulfill_scratch(int64_t Pp, int T, int D)
+{
+    const size_t nblocks = (size_t)((Pp + kCompactChunk - 1) / kCompactChunk) + 1;
+    return 32768 + (size_t)Pp + sizeof(int32_t) * (size_t)Pp * 4 + sizeof(uint32_t) * (size_t)((Pp + 31) / 32) +
+           sizeof(int) * (kMaxStagesPerPass + 8) + sizeof(int) * nblocks + sizeof(double) * (size_t)T * D + 256 * 16;
+}
+
+// req row of pending pod p is req[(row_map ? row_map[p] : p) * D]
+static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int32_t *row_map, int64_t Pp,
+                                  int64_t num_listed, int D, const double *unit_host, const int32_t *pool_actual,
+                                  const int32_t *pool_max, const uint8_t *pool_ignored, int T, int64_t over_provision,
+                                  int64_t *out_new_size, int64_t *out_units_needed, int64_t *out_bins_opened,
+                                  int32_t *out_acc_pool, int32_t *out_bin_of, int64_t *out_unaccounted,
+                                  uint64_t *out_evals, cudaStream_t st)
+{
+    for (int i = 0; i < T * D; ++i)
+        if (!std::isfinite(unit_host[i])) return fail(ctx, ACSFIT_E_DOMAIN, "fulfill_pending: non-finite unit capacity");
+    const int64_t alive_words = (Pp + 31) / 32;
+    const int nblocks = (int)((Pp + kCompactChunk - 1) / kCompactChunk) + 1;
+    TAKE(elig, uint8_t, Pp);
+    TAKE(list_a, int32_t, Pp);
+    TAKE(list_b, int32_t, Pp);
+    TAKE(placed, int32_t, Pp);
+    TAKE(cur_bin, int32_t, Pp);
+    TAKE(alive, uint32_t, alive_words);
+    TAKE(sync_words, int, kMaxStagesPerPass + 8);
+    TAKE(block_counts, int, nblocks);
+    TAKE(unit_dev, double, (size_t)T * D);
+    TAKE(total_dev, int64_t, 1);
+    TAKE(evals_dev, unsigned long long, 1);
+    TAKE(count_dev, unsigned long long, 1);
+    TAKE(max_bin_dev, int, 1);
+    int *ticket = sync_words, *status = sync_words + 1, *drained = sync_words + 2, *progress = sync_words + 8;
+
+    if (T > 0) CUDA_TRY(cudaMemcpyAsync(unit_dev, unit_host, sizeof(double) * T * D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(evals_dev, 0, sizeof(unsigned long long), st));
+    if (Pp > 0) {
+        fill_i32_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(out_acc_pool, Pp, -1);
+        fill_i32_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(out_bin_of, Pp, -1);
+        ctx->launches += 2;
+    }
+
+    uint64_t evals = 0;
+    int64_t num_unaccounted = num_listed;  // scaler.py:120 (duplicates counted)
+    int64_t unique_unaccounted = Pp;
+    float total_ms = 0.f;
+
+    for (int t = 0; t < T; ++t) {
+        out_new_size[t] = pool_actual[t];  // scaler.py:125-126
+        out_units_needed[t] = -1;
+        out_bins_opened[t] = 0;
+        if (pool_ignored[t] || !num_unaccounted) continue;  // scaler.py:128-129
+
+        int64_t nb = 0, E = 0;
+        if (Pp > 0) {
+            // pool gate (scaler.py:134) over the not-yet-accounted pods -> ordered list of eligible pods
+            eligible_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(req, row_map, Pp, D, unit_dev + (size_t)t * D,
+                                                                   out_acc_pool, elig);
+            ++ctx->launches;
+            evals += (uint64_t)unique_unaccounted;
+            TRY(compact(ctx, FlagPred{elig}, Pp, nullptr, list_a, block_counts, total_dev, &E, st));
+        }
+        if (E > 0) {
+            fill_i32_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(cur_bin, Pp, -1);
+            ++ctx->launches;
+            CUDA_TRY(cudaMemsetAsync(max_bin_dev, 0xFF, sizeof(int), st));  // -1
+            int32_t *list = list_a, *next = list_b;
+            int64_t M = E, bin_base = 0;
+            while (M > 0) {
+                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass);  // at most one bin per pod
+                CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
+                fill_alive_kernel<<<grid_for(ctx, (M + 31) / 32, 256), 256, 0, st>>>(alive, M);
+                fill_i32_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(placed, M, -1);
+                ctx->launches += 2;
+                PipelineParams pp;
+                memset(&pp, 0, sizeof pp);
+                pp.req = req;
+                pp.pod_idx = list;
+                pp.row_map = row_map;
+                pp.M = M;
+                pp.alive = alive;
+                pp.placed = placed;
+                pp.unit = unit_dev + (size_t)t * D;
+                pp.bin_base = bin_base;
+                pp.node_lo = bin_base;
+                pp.node_hi = bin_base + (int64_t)plan.stages * plan.Tn;
+                pp.Tn = plan.Tn;
+                pp.NS = plan.NS;
+                pp.num_tiles = (int)((M + kTile - 1) / kTile);
+                pp.ticket = ticket;
+                pp.progress = progress;
+                pp.status = status;
+                pp.drained = drained;
+                pp.evals = evals_dev;
+                pp.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+                if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+                TRY(launch_pipeline<true>(ctx, D, pp, plan.stages, st));
+                if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+                scatter_bins_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(list, placed, M, cur_bin, out_bin_of,
+                                                                          max_bin_dev);
+                ++ctx->launches;
+                TRY(check_pipeline_status(ctx, status, st));
+                if (ctx->timing) {
+                    float ms = 0.f;
+                    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+                    total_ms += ms;
+                }
+                ctx->last_stages += plan.stages;
+                ctx->last_tiles += pp.num_tiles;
+                // pods that fitted none of this pass's bins go on to a pass of fresh bins
+                int64_t left = 0;
+                TRY(compact(ctx, BitPred{alive}, M, list, next, block_counts, total_dev, &left, st));
+                bin_base += (int64_t)plan.stages * plan.Tn;
+                std::swap(list, next);
+                M = left;
+            }
+            int max_bin = -1;
+            CUDA_TRY(cudaMemcpyAsync(&max_bin, max_bin_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            nb = (int64_t)max_bin + 1;  // opened bins form a prefix
+        }
+        // scaler.py:152-167
+        const int64_t needed = nb + over_provision;
+        const int64_t room = (int64_t)pool_max[t] - (int64_t)pool_actual[t];
+        const int64_t unavailable = std::max<int64_t>(0, needed - room);
+        const int64_t requested = needed - unavailable;
+        out_units_needed[t] = needed;
+        out_bins_opened[t] = nb;
+        out_new_size[t] = (int64_t)pool_actual[t] + requested;
+        const int64_t take = std::min(nb, requested);  // range(min(len(bins), units_requested))
+        if (take > 0 && E > 0) {
+            CUDA_TRY(cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), st));
+            account_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(
+                cur_bin, Pp, (int32_t)std::min<int64_t>(take, INT32_MAX), t, out_acc_pool, count_dev);
+            ++ctx->launches;
+            unsigned long long cnt = 0;
+            CUDA_TRY(cudaMemcpyAsync(&cnt, count_dev, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            num_unaccounted -= (int64_t)cnt;
+            unique_unaccounted -= (int64_t)cnt;
+        }
+    }
+    unsigned long long bin_evals = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bin_evals, evals_dev, sizeof bin_evals, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    evals += bin_evals;
+    *out_unaccounted = num_unaccounted;
+    if (out_evals) *out_evals = evals;
+    ctx->last_ms += total_ms;
+    ctx->last_decisions += evals;
+    return ACSFIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ABI: device-pointer entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" acsfit_status acsfit_feasible_mask(acsfit_ctx *ctx, const double *req, int64_t P, int D,
+                                              const double *unit, int T, uint8_t *out_mask,
+                                              uint64_t *out_evals, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || T < 0 || T > ACSFIT_MAX_POOLS || (P > 0 && (!req || !out_mask)) || (T > 0 && !unit))
+        return fail(ctx, ACSFIT_E_INVALID, "feasible_mask: bad arguments");
+    if (out_evals) CUDA_TRY(cudaMemsetAsync(out_evals, 0, sizeof(uint64_t), st));
+    if (P == 0) return ACSFIT_OK;
+    feasible_mask_kernel<<<grid_for(ctx, P, 256), 256, sizeof(double) * std::max(1, T * D), st>>>(
+        req, P, D, unit, T, out_mask, reinterpret_cast<unsigned long long *>(out_evals));
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_occupancy(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                          const double *req_run, int64_t N, int D, double *used_inout,
+                                          acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || (N > 0 && (!row_ptr || !used_inout)))
+        return fail(ctx, ACSFIT_E_INVALID, "occupancy: bad arguments");
+    if (N == 0) return ACSFIT_OK;
+    occupancy_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(row_ptr, run_idx, req_run, N, D, used_inout);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_first_fit_nodes(acsfit_ctx *ctx, const double *req, int64_t req_rows,
+                                                const int32_t *pod_idx, int64_t P, int D,
+                                                const double *cap_type, const int32_t *node_type,
+                                                double *used_inout, int64_t N, int32_t *out_placed,
+                                                uint64_t *out_decisions, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || N < 0 || req_rows < 0 || P > INT32_MAX || N > INT32_MAX || (!pod_idx && P > req_rows) ||
+        (P > 0 && (!req || !out_placed)) || (N > 0 && (!cap_type || !node_type || !used_inout)))
+        return fail(ctx, ACSFIT_E_INVALID, "first_fit_nodes: bad arguments");
+    if (!pipeline_dims_ok(D))
+        return fail(ctx, ACSFIT_E_INVALID, "first_fit_nodes: D=%d, need 2/4/8/16 (zero columns are neutral)", D);
+    reset_stats(ctx);
+    TRY(arena_reserve(ctx, first_fit_scratch(ctx, P, N) + 1024, st));
+    ctx->arena_off = 0;
+    TAKE(flag, int, 1);
+    TRY(check_domain(ctx, req, req_rows * D, flag, st, "req"));
+    return first_fit_impl(ctx, req, pod_idx, P, D, cap_type, node_type, used_inout, N, out_placed,
+                          reinterpret_cast<unsigned long long *>(out_decisions), st);
+}
+
+extern "C" acsfit_status acsfit_fulfill_pending(acsfit_ctx *ctx, const double *req, int64_t Pp,
+                                                int64_t num_listed, int D, const double *unit,
+                                                const int32_t *pool_actual, const int32_t *pool_max,
+                                                const uint8_t *pool_ignored, int T, int64_t over_provision,
+                                                int64_t *out_new_size, int64_t *out_units_needed,
+                                                int64_t *out_bins_opened, int32_t *out_acc_pool,
+                                                int32_t *out_bin_of, int64_t *out_unaccounted,
+                                                uint64_t *out_evals, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Pp < 0 || Pp > INT32_MAX || num_listed < Pp || T < 0 || T > ACSFIT_MAX_POOLS ||
+        (Pp > 0 && (!req || !out_acc_pool || !out_bin_of)) ||
+        (T > 0 && (!unit || !pool_actual || !pool_max || !pool_ignored || !out_new_size || !out_units_needed ||
+                   !out_bins_opened)) ||
+        !out_unaccounted)
+        return fail(ctx, ACSFIT_E_INVALID, "fulfill_pending: bad arguments");
+    if (!pipeline_dims_ok(D))
+        return fail(ctx, ACSFIT_E_INVALID, "fulfill_pending: D=%d, need 2/4/8/16 (zero columns are neutral)", D);
+    reset_stats(ctx);
+    TRY(arena_reserve(ctx, fulfill_scratch(Pp, T, D) + 1024, st));
+    ctx->arena_off = 0;
+    TAKE(flag, int, 1);
+    TRY(check_domain(ctx, req, Pp * D, flag, st, "req"));
+    return fulfill_impl(ctx, req, nullptr, Pp, num_listed, D, unit, pool_actual, pool_max, pool_ignored, T,
+                        over_provision, out_new_size, out_units_needed, out_bins_opened, out_acc_pool, out_bin_of,
+                        out_unaccounted, out_evals, st);
+}
+
+extern "C" acsfit_status acsfit_node_states(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                            const double *req_run, const uint8_t *flags_run,
+                                            const double *cap_type, const int32_t *node_type,
+                                            const uint8_t *node_flags, const int64_t *node_age, int64_t N,
+                                            int D, int any_pending, const int64_t *idle_threshold, int S,
+                                            uint8_t *out_state, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || S < 1 || S > 64 || !idle_threshold ||
+        (N > 0 && (!row_ptr || !cap_type || !node_type || !node_flags || !node_age || !out_state)))
+        return fail(ctx, ACSFIT_E_INVALID, "node_states: bad arguments");
+    if (N == 0) return ACSFIT_OK;
+    TRY(arena_reserve(ctx, 8192, st));
+    ctx->arena_off = 0;
+    TAKE(thr_dev, int64_t, S);
+    CUDA_TRY(cudaMemcpyAsync(thr_dev, idle_threshold, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
+    node_states_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type,
+                                                             node_type, node_flags, node_age, N, D, any_pending,
+                                                             thr_dev, S, out_state);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));  // idle_threshold is a host buffer
+    return ACSFIT_OK;
+}
+
+static acsfit_status maintain_actions_impl(acsfit_ctx *ctx, uint8_t *io_state, const int32_t *node_pool, int64_t N,
+                                           const int64_t *budget0, const uint8_t *pool_scalable, int T, int dry_run,
+                                           uint8_t *out_action, cudaStream_t st)
+{
+    const int chunks = (int)((N + kMaintChunk - 1) / kMaintChunk);
+    const int Tq = std::max(T, 1);
+    TAKE(budget_dev, long long, Tq);
+    TAKE(scal_dev, uint8_t, Tq);
+    TAKE(counts, int, (size_t)chunks * Tq);
+    if (T > 0) {
+        CUDA_TRY(cudaMemcpyAsync(budget_dev, budget0, sizeof(long long) * T, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(scal_dev, pool_scalable, T, cudaMemcpyHostToDevice, st));
+    }
+    const int *rank_base = nullptr;
+    if (!dry_run && T > 0) {
+        maintain_count_kernel<<<chunks, kMaintBlock, sizeof(int) * Tq, st>>>(io_state, node_pool, N, scal_dev, T, counts);
+        maintain_scan_kernel<<<(T + 63) / 64, 64, 0, st>>>(counts, chunks, T);
+        ctx->launches += 2;
+        rank_base = counts;
+    }
+    maintain_apply_kernel<<<chunks, kMaintBlock, sizeof(int) * Tq, st>>>(io_state, node_pool, N, budget_dev, scal_dev,
+                                                                        T, dry_run, rank_base, out_action);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));  // budget0 / pool_scalable are host buffers
+    return ACSFIT_OK;
+}
+
+static size_t maintain_scratch(int64_t N, int T)
+{
+    const size_t chunks = (size_t)((N + kMaintChunk - 1) / kMaintChunk) + 1;
+    const size_t Tq = (size_t)std::max(T, 1);
+    return 8192 + sizeof(int) * chunks * Tq + sizeof(long long) * Tq + Tq;
+}
+
+extern "C" acsfit_status acsfit_maintain_actions(acsfit_ctx *ctx, uint8_t *io_state, const int32_t *node_pool,
+                                                 int64_t N, const int64_t *budget0, const uint8_t *pool_scalable,
+                                                 int T, int dry_run, uint8_t *out_action, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || T < 0 || T > ACSFIT_MAX_POOLS || (T > 0 && (!budget0 || !pool_scalable)) ||
+        (N > 0 && (!io_state || !node_pool || !out_action)))
+        return fail(ctx, ACSFIT_E_INVALID, "maintain_actions: bad arguments");
+    if (N == 0) return ACSFIT_OK;
+    TRY(arena_reserve(ctx, maintain_scratch(N, T), st));
+    ctx->arena_off = 0;
+    return maintain_actions_impl(ctx, io_state, node_pool, N, budget0, pool_scalable, T, dry_run, out_action, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused scale-up tick: get_pods_to_schedule + get_pending_pods + fulfill_pending
+// (reference cluster.py:169-175, :206-215) on DEVICE buffers
+// ---------------------------------------------------------------------------------------------
+namespace {
+// placed_all[p] = -2 (infeasible) | -1 (pending) | node ; from the feasible list and its placements
+__global__ void expand_placed_kernel(const uint8_t *feasible, int64_t P, int32_t *placed_all)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
+        placed_all[i] = feasible[i] ? -1 : -2;
+}
+__global__ void scatter_i32_kernel(const int32_t *list, const int32_t *vals, int64_t n, int32_t *out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[list[i]] = vals[i];
+}
+struct NegPred {
+    const int32_t *v;
+    __device__ bool operator()(int64_t i) const { return v[i] < 0; }
+};
+}  // namespace
+
+static size_t scale_up_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N, int T, int D)
+{
+    const size_t nblocks = (size_t)((P + kCompactChunk - 1) / kCompactChunk) + 1;
+    return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + sizeof(int32_t) * (size_t)P * 5 +
+           sizeof(int) * nblocks + sizeof(double) * (size_t)T * D + 65536;
+}
+
+static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P, int D, const double *unit_all_host,
+                                   const double *unit_ordered_host, const int32_t *pool_actual,
+                                   const int32_t *pool_max, const uint8_t *pool_ignored, int T, int64_t over_provision,
+                                   const double *cap_type, const int32_t *node_type, double *used, int64_t N,
+                                   uint8_t *out_feasible, int32_t *out_placed, int64_t *out_new_size,
+                                   int64_t *out_units_needed, int64_t *out_bins_opened, int32_t *out_acc_pool,
+                                   uint64_t *out_counters, cudaStream_t st)
+{
+    const int nblocks = (int)((P + kCompactChunk - 1) / kCompactChunk) + 1;
+    TAKE(flag, int, 1);
+    TAKE(unit_all_dev, double, (size_t)T * D);
+    TAKE(list_f, int32_t, P);      // pods to schedule (feasible), in order
+    TAKE(placed_f, int32_t, P);    // their placements
+    TAKE(list_p, int32_t, P);      // pending pods (pod numbers), in order
+    TAKE(acc_p, int32_t, P);
+    TAKE(bin_p, int32_t, P);
+    TAKE(block_counts, int, nblocks);
+    TAKE(total_dev, int64_t, 1);
+    TAKE(evals_dev, unsigned long long, 2);
+
+    uint64_t decisions = 0;
+    TRY(check_domain(ctx, req, P * D, flag, st, "req"));
+    if (T > 0) CUDA_TRY(cudaMemcpyAsync(unit_all_dev, unit_all_host, sizeof(double) * T * D, cudaMemcpyHostToDevice, st));
+    // get_pods_to_schedule (cluster.py:217-240)
+    CUDA_TRY(cudaMemsetAsync(evals_dev, 0, 2 * sizeof(unsigned long long), st));
+    int64_t F = 0;
+    if (P > 0) {
+        feasible_mask_kernel<<<grid_for(ctx, P, 256), 256, sizeof(double) * std::max(1, T * D), st>>>(
+            req, P, D, unit_all_dev, T, out_feasible, evals_dev);
+        expand_placed_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_feasible, P, out_placed);
+        fill_i32_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_acc_pool, P, -1);
+        ctx->launches += 3;
+        TRY(compact(ctx, FlagPred{out_feasible}, P, nullptr, list_f, block_counts, total_dev, &F, st));
+    }
+    // get_pending_pods (cluster.py:184-204)
+    int64_t Pn = 0;
+    if (F > 0) {
+        TRY(first_fit_impl(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1, st));
+        scatter_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(list_f, placed_f, F, out_placed);
+        ++ctx->launches;
+        TRY(compact(ctx, NegPred{placed_f}, F, list_f, list_p, block_counts, total_dev, &Pn, st));
+    }
+    unsigned long long ev[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(ev, evals_dev, sizeof ev, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    decisions += ev[0] + ev[1];
+    // scale(): fulfill_pending only when something is pending (cluster.py:214-215)
+    int64_t unaccounted = 0;
+    for (int t = 0; t < T; ++t) {
+        out_new_size[t] = pool_actual[t];
+        out_units_needed[t] = -1;
+        out_bins_opened[t] = 0;
+    }
+    if (Pn > 0) {
+        uint64_t fe = 0;
+        TRY(fulfill_impl(ctx, req, list_p, Pn, Pn, D, unit_ordered_host, pool_actual, pool_max, pool_ignored, T,
+                         over_provision, out_new_size, out_units_needed, out_bins_opened, acc_p, bin_p, &unaccounted,
+                         &fe, st));
+        decisions += fe;
+        scatter_i32_kernel<<<grid_for(ctx, Pn, 256), 256, 0, st>>>(list_p, acc_p, Pn, out_acc_pool);
+        ++ctx->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    out_counters[0] = (uint64_t)F;
+    out_counters[1] = (uint64_t)Pn;
+    out_counters[2] = (uint64_t)unaccounted;
+    out_counters[3] = decisions;
+    return ACSFIT_OK;
+}
+
+static acsfit_status scale_up_check(acsfit_ctx *ctx, const void *req, int64_t P, int D, const void *unit_all,
+                                    const void *unit_ordered, const void *pa, const void *pm, const void *pi, int T,
+                                    const void *cap_type, const void *node_type, const void *used, int64_t N,
+                                    const void *o1, const void *o2, const void *o3, const void *o4, const void *o5,
+                                    const void *o6, const void *o7)
+{
+    if (P < 0 || N < 0 || P > INT32_MAX || N > INT32_MAX || T < 0 || T > ACSFIT_MAX_POOLS ||
+        (P > 0 && (!req || !o1 || !o2 || !o6)) || (T > 0 && (!unit_all || !unit_ordered || !pa || !pm || !pi || !o3 || !o4 || !o5)) ||
+        (N > 0 && (!cap_type || !node_type || !used)) || !o7)
+        return fail(ctx, ACSFIT_E_INVALID, "scale_up: bad arguments");
+    if (!pipeline_dims_ok(D))
+        return fail(ctx, ACSFIT_E_INVALID, "scale_up: D=%d, need 2/4/8/16 (zero columns are neutral)", D);
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_scale_up(acsfit_ctx *ctx, const double *req, int64_t P, int D,
+                                         const double *unit_all, const double *unit_ordered,
+                                         const int32_t *pool_actual, const int32_t *pool_max,
+                                         const uint8_t *pool_ignored, int T, int64_t over_provision,
+                                         const double *cap_type, const int32_t *node_type, double *used_inout,
+                                         int64_t N, uint8_t *out_feasible, int32_t *out_placed,
+                                         int64_t *out_new_size, int64_t *out_units_needed, int64_t *out_bins_opened,
+                                         int32_t *out_acc_pool, uint64_t *out_counters, acsfit_stream_t stream)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(scale_up_check(ctx, req, P, D, unit_all, unit_ordered, pool_actual, pool_max, pool_ignored, T, cap_type,
+                       node_type, used_inout, N, out_feasible, out_placed, out_new_size, out_units_needed,
+                       out_bins_opened, out_acc_pool, out_counters));
+    reset_stats(ctx);
+    TRY(arena_reserve(ctx, scale_up_scratch(ctx, P, N, T, D), st));
+    ctx->arena_off = 0;
+    return scale_up_impl(ctx, req, P, D, unit_all, unit_ordered, pool_actual, pool_max, pool_ignored, T,
+                         over_provision, cap_type, node_type, used_inout, N, out_feasible, out_placed, out_new_size,
+                         out_units_needed, out_bins_opened, out_acc_pool, out_counters, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------
+static acsfit_status hbuf_reserve(acsfit_ctx *ctx, size_t bytes)
+{
+    ctx->hbuf_off = 0;
+    if (bytes <= ctx->hbuf_cap) return ACSFIT_OK;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (ctx->hbuf) CUDA_TRY(cudaFree(ctx->hbuf));
+    ctx->hbuf = nullptr;
+    ctx->hbuf_cap = 0;
+    const size_t cap = align_up(bytes + bytes / 4, 1 << 20);
+    CUDA_TRY(cudaMalloc(&ctx->hbuf, cap));
+    ctx->hbuf_cap = cap;
+    return ACSFIT_OK;
+}
+
+template <typename T>
+static T *hbuf_take(acsfit_ctx *ctx, size_t count)
+{
+    const size_t off = align_up(ctx->hbuf_off, 256);
+    const size_t bytes = sizeof(T) * std::max<size_t>(count, 1);
+    if (off + bytes > ctx->hbuf_cap) return nullptr;
+    ctx->hbuf_off = off + bytes;
+    return reinterpret_cast<T *>(ctx->hbuf + off);
+}
+
+#define HTAKE(var, T, count)                                                                \
+    T *var = hbuf_take<T>(ctx, (count));                                                    \
+    if (!var) return fail(ctx, ACSFIT_E_NOMEM, "host-entry device buffer too small for %s", #var)
+
+#define H2D(dst, src, bytes)                                                                \
+    do {                                                                                    \
+        if ((bytes) > 0) CUDA_TRY(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, st)); \
+    } while (0)
+#define D2H(dst, src, bytes)                                                                \
+    do {                                                                                    \
+        if ((bytes) > 0) CUDA_TRY(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st)); \
+    } while (0)
+
+extern "C" acsfit_status acsfit_scale_up_host(acsfit_ctx *ctx, const double *req, int64_t P, int D,
+                                              const double *unit_all, const double *unit_ordered,
+                                              const int32_t *pool_actual, const int32_t *pool_max,
+                                              const uint8_t *pool_ignored, int T, int64_t over_provision,
+                                              const double *cap_type, int K, const int32_t *node_type,
+                                              double *used_inout, int64_t N, uint8_t *out_feasible,
+                                              int32_t *out_placed, int64_t *out_new_size,
+                                              int64_t *out_units_needed, int64_t *out_bins_opened,
+                                              int32_t *out_acc_pool, uint64_t *out_counters)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = nullptr;
+    if (K < 0) return fail(ctx, ACSFIT_E_INVALID, "scale_up_host: K < 0");
+    TRY(scale_up_check(ctx, req, P, D, unit_all, unit_ordered, pool_actual, pool_max, pool_ignored, T, cap_type,
+                       node_type, used_inout, N, out_feasible, out_placed, out_new_size, out_units_needed,
+                       out_bins_opened, out_acc_pool, out_counters));
+    for (int i = 0; i < K * D; ++i)
+        if (!std::isfinite(cap_type[i])) return fail(ctx, ACSFIT_E_DOMAIN, "scale_up_host: non-finite capacity");
+    reset_stats(ctx);
+    const size_t bytes = sizeof(double) * ((size_t)P * D + (size_t)K * D + (size_t)N * D) +
+                         sizeof(int32_t) * ((size_t)N + 2 * (size_t)P) + (size_t)P + 16 * 256;
+    TRY(hbuf_reserve(ctx, bytes));
+    HTAKE(d_req, double, (size_t)P * D);
+    HTAKE(d_cap, double, (size_t)K * D);
+    HTAKE(d_used, double, (size_t)N * D);
+    HTAKE(d_type, int32_t, N);
+    HTAKE(d_placed, int32_t, P);
+    HTAKE(d_acc, int32_t, P);
+    HTAKE(d_feas, uint8_t, P);
+    H2D(d_req, req, sizeof(double) * (size_t)P * D);
+    H2D(d_cap, cap_type, sizeof(double) * (size_t)K * D);
+    H2D(d_used, used_inout, sizeof(double) * (size_t)N * D);
+    H2D(d_type, node_type, sizeof(int32_t) * (size_t)N);
+    TRY(arena_reserve(ctx, scale_up_scratch(ctx, P, N, T, D), st));
+    ctx->arena_off = 0;
+    TRY(scale_up_impl(ctx, d_req, P, D, unit_all, unit_ordered, pool_actual, pool_max, pool_ignored, T, over_provision,
+                      d_cap, d_type, d_used, N, d_feas, d_placed, out_new_size, out_units_needed, out_bins_opened,
+                      d_acc, out_counters, st));
+    D2H(out_feasible, d_feas, (size_t)P);
+    D2H(out_placed, d_placed, sizeof(int32_t) * (size_t)P);
+    D2H(out_acc_pool, d_acc, sizeof(int32_t) * (size_t)P);
+    D2H(used_inout, d_used, sizeof(double) * (size_t)N * D);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                              const double *req_run, const uint8_t *flags_run, int64_t R,
+                                              const double *cap_type, int K, const int32_t *node_type,
+                                              const uint8_t *node_flags, const int64_t *node_age,
+                                              const int32_t *node_pool, int64_t N, int D, int any_pending,
+                                              int64_t idle_threshold, const int64_t *budget0,
+                                              const uint8_t *pool_scalable, int T, int dry_run,
+                                              uint8_t *out_state, uint8_t *out_action)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = nullptr;
+    if (N < 0 || R < 0 || K < 0 || T < 0 || T > ACSFIT_MAX_POOLS ||
+        (N > 0 && (!row_ptr || !cap_type || !node_type || !node_flags || !node_age || !node_pool || !out_state || !out_action)) ||
+        (R > 0 && (!req_run || !flags_run)) || (T > 0 && (!budget0 || !pool_scalable)))
+        return fail(ctx, ACSFIT_E_INVALID, "maintain_host: bad arguments");
+    if (N == 0) return ACSFIT_OK;
+    const int64_t nnz = row_ptr[N];
+    if (nnz < 0 || (nnz > 0 && !run_idx)) return fail(ctx, ACSFIT_E_INVALID, "maintain_host: bad CSR");
+    const size_t bytes = sizeof(int64_t) * (2 * (size_t)N + 2) + sizeof(int32_t) * ((size_t)nnz + 2 * (size_t)N) +
+                         sizeof(double) * ((size_t)R * D + (size_t)K * D) + (size_t)R + 3 * (size_t)N + 16 * 256;
+    TRY(hbuf_reserve(ctx, bytes));
+    HTAKE(d_ptr, int64_t, (size_t)N + 1);
+    HTAKE(d_age, int64_t, N);
+    HTAKE(d_thr, int64_t, 1);
+    HTAKE(d_req, double, (size_t)R * D);
+    HTAKE(d_cap, double, (size_t)K * D);
+    HTAKE(d_idx, int32_t, nnz);
+    HTAKE(d_type, int32_t, N);
+    HTAKE(d_pool, int32_t, N);
+    HTAKE(d_pflags, uint8_t, R);
+    HTAKE(d_nflags, uint8_t, N);
+    HTAKE(d_state, uint8_t, N);
+    HTAKE(d_action, uint8_t, N);
+    H2D(d_ptr, row_ptr, sizeof(int64_t) * ((size_t)N + 1));
+    H2D(d_age, node_age, sizeof(int64_t) * (size_t)N);
+    H2D(d_thr, &idle_threshold, sizeof(int64_t));
+    H2D(d_req, req_run, sizeof(double) * (size_t)R * D);
+    H2D(d_cap, cap_type, sizeof(double) * (size_t)K * D);
+    H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
+    H2D(d_type, node_type, sizeof(int32_t) * (size_t)N);
+    H2D(d_pool, node_pool, sizeof(int32_t) * (size_t)N);
+    H2D(d_pflags, flags_run, (size_t)R);
+    H2D(d_nflags, node_flags, (size_t)N);
+    node_states_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(d_ptr, d_idx, d_req, d_pflags, d_cap, d_type, d_nflags,
+                                                             d_age, N, D, any_pending, d_thr, 1, d_state);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    TRY(arena_reserve(ctx, maintain_scratch(N, T), st));
+    ctx->arena_off = 0;
+    TRY(maintain_actions_impl(ctx, d_state, d_pool, N, budget0, pool_scalable, T, dry_run, d_action, st));
+    D2H(out_state, d_state, (size_t)N);
+    D2H(out_action, d_action, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ACSFIT_OK;
+}

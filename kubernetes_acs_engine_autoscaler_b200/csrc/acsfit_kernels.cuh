@@ -1,0 +1,405 @@
+// acsfit_kernels.cuh -- sm_100a kernels of the pod-fit path (no tensor cores: this is
+// compare / reduce work on float64).
+//
+// The centrepiece is firstfit_pipeline_kernel: an EXACT, order-preserving parallelisation of
+// the reference's two sequential first-fit loops
+//     Cluster.get_pending_pods   autoscaler/cluster.py:184-204   (nodes, state = used)
+//     Scaler.fulfill_pending     autoscaler/scaler.py:131-147    (bins,  state = remaining)
+// as a systolic pipeline over the node (bin) axis:
+//
+//   * the node list is cut into consecutive STAGES of Tn nodes; one CTA owns one stage and
+//     keeps that stage's per-node thresholds (acsfit_math.cuh) in shared memory / registers;
+//   * the ordered pod list flows through the stages in TILES of 256 pods.  Stage s may
+//     process tile i once stage s-1 has published it (a release/acquire counter in global
+//     memory) - stage s works on tile i while stage s-1 already works on tile i+1;
+//   * inside a tile, every (alive pod, node) pair of the stage is evaluated in parallel under
+//     the tile-start state (pure DSETP work, pod rows broadcast from shared memory).  Because
+//     a node only ever fills up (requests are >= 0, rounding is monotone) a pod that fits no
+//     node of the stage under the tile-start state fits none later either: it is forwarded
+//     untouched.  The few pods that do hit are resolved by one warp strictly in pod order
+//     against the live thresholds (ballot + ffs over 32-node chunks), which is exactly the
+//     reference's loop restricted to this stage's nodes;
+//   * a pod that is placed has its alive bit cleared; pods still alive after the last stage
+//     are the pending pods (nodes) / flow into the next pass of fresh bins (bins).
+//
+// Stage numbers are taken from an atomic ticket at CTA start, so stage s only ever waits for
+// a CTA that is already running or finished: no co-residency assumption, no deadlock, and
+// more stages than resident CTAs simply run as successive waves.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "acsfit_math.cuh"
+
+namespace acsfit {
+
+constexpr int kTile = 256;         // pods per tile == threads per CTA
+constexpr int kThreads = 256;
+constexpr int kNodesPerThread = 4; // K: node rows a thread keeps in registers in the scan
+constexpr int kMaxStageNodes = kThreads * kNodesPerThread;  // 1024
+constexpr unsigned kNoCand = 0xFFFFFFFFu;
+constexpr int kMaxDims = 16;
+
+struct PipelineParams {
+    // pod side
+    const double *req;      // rows of D doubles
+    const int32_t *pod_idx; // list entry -> pod number, or nullptr (identity)
+    const int32_t *row_map; // pod number -> row of req, or nullptr (identity)
+    int64_t M;              // list length
+    uint32_t *alive;        // ceil(M/32) words, bit = still unplaced (in/out)
+    int32_t *placed;        // M entries, written with the GLOBAL node / bin index on placement
+    // node side (nodes mode)
+    const double *cap_type; // K x D
+    const int32_t *node_type;
+    double *used;           // N x D (in/out)
+    // bin side (bins mode)
+    const double *unit;     // D doubles (device)
+    int64_t bin_base;       // global index of the first bin of this pass
+    // geometry
+    int64_t node_lo;        // first node (local numbering of stage 0 starts here)
+    int64_t node_hi;        // one past the last node (nodes mode) / bin_base + stages*Tn (bins)
+    int Tn;                 // nodes per stage (NS * K)
+    int NS;                 // node slots = Tn / K (power of two, <= kThreads)
+    int num_tiles;
+    // synchronisation
+    int *ticket;            // 1 int, zeroed
+    int *progress;          // num_stages ints, zeroed: tiles published by the stage
+    int *status;            // 1 int, zeroed: != 0 -> abort (watchdog)
+    int *drained;           // 1 int, zeroed: set by the first stage that forwards no pod at all
+    unsigned long long *evals; // bins mode: credited bin tests (atomicAdd)
+    unsigned long long watchdog_ns;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int D>
+__device__ __forceinline__ void load_row(double (&r)[D], const double *src)
+{
+    static_assert(D % 2 == 0, "rows are padded to an even number of dims");
+#pragma unroll
+    for (int d = 0; d < D; d += 2) {
+        double2 v = *reinterpret_cast<const double2 *>(src + d);
+        r[d] = v.x;
+        r[d + 1] = v.y;
+    }
+}
+
+// dynamic shared memory layout (doubles first for alignment)
+template <int D>
+struct PipelineSmem {
+    static __host__ __device__ size_t bytes(int Tn)
+    {
+        return sizeof(double) * ((size_t)kTile * D + (size_t)D * Tn)  // rows, thr
+               + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ +
+                                     kMaxStageNodes / 32 /*opened*/ + 8 /*warp counts*/ + 4)
+               + sizeof(unsigned short) * kTile /*slot_of*/;
+    }
+};
+
+template <int D, bool BINS>
+__global__ void __launch_bounds__(kThreads)
+firstfit_pipeline_kernel(const PipelineParams p)
+{
+    constexpr int K = kNodesPerThread;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *rows = reinterpret_cast<double *>(smem_raw);        // [kTile][D]
+    double *thr_s = rows + (size_t)kTile * D;                   // [D][Tn]
+    unsigned *cand = reinterpret_cast<unsigned *>(thr_s + (size_t)D * p.Tn);  // [kTile]
+    unsigned *hitmask = cand + kTile;                           // [kTile/32]
+    unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]
+    unsigned *opened = alive_w + kTile / 32;                    // [kMaxStageNodes/32]
+    unsigned *wcount = opened + kMaxStageNodes / 32;            // [8]
+    unsigned *misc = wcount + 8;                                // [4]: 0 = stage, 1 = abort flag, 2 = drained
+    unsigned short *slot_of = reinterpret_cast<unsigned short *>(misc + 4);  // [kTile]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int Tn = p.Tn;
+
+    if (tid == 0) {
+        misc[0] = (unsigned)atomicAdd(p.ticket, 1);
+        misc[1] = 0;
+        misc[2] = 0;
+    }
+    __syncthreads();
+    const int stage = (int)misc[0];
+    const int64_t stage_lo = p.node_lo + (int64_t)stage * Tn;   // global index of local node 0
+    const int n_valid = (int)max((int64_t)0, min((int64_t)Tn, p.node_hi - stage_lo));
+
+    // ---- stage start: thresholds of this stage's nodes into shared memory ------------------
+    for (int i = tid; i < Tn * D; i += kThreads) {
+        const int n = i / D, d = i - n * D;
+        double t = -1.0;  // padding nodes never fit
+        if (n < n_valid) {
+            if (BINS) {
+                t = p.unit[d];  // untouched bin: remaining == unit (scaler.py:145-146)
+            } else {
+                const int64_t gn = stage_lo + n;
+                t = node_threshold(p.cap_type[(size_t)p.node_type[gn] * D + d], p.used[(size_t)gn * D + d]);
+            }
+        }
+        thr_s[(size_t)d * Tn + n] = t;
+    }
+    for (int i = tid; i < kMaxStageNodes / 32; i += kThreads) opened[i] = 0;
+    __syncthreads();
+
+    const int NS = p.NS;
+    const int slot = tid & (NS - 1);
+    const int group = tid / NS;
+    const int PG = kThreads / NS;
+    unsigned long long my_evals = 0;
+    long long forwarded = 0;  // (thread 0) pods this stage passed on to the next one
+    const unsigned long long t_start = global_timer_ns();
+
+    for (int tile = 0; tile < p.num_tiles; ++tile) {
+        // ---- wait until the previous stage has published this tile -------------------------
+        if (stage > 0) {
+            if (tid == 0) {
+                const int *flag = p.progress + (stage - 1);
+                unsigned spins = 0;
+                if (*(volatile int *)p.drained) {
+                    // an earlier stage finished with nothing left alive: every remaining tile is
+                    // empty, publish them all at once and leave
+                    misc[2] = 1;
+                } else
+                while (ld_acquire(flag) <= tile) {
+                    if ((++spins & 63u) == 0) {
+                        if (*(volatile int *)p.status != 0 ||
+                            global_timer_ns() - t_start > p.watchdog_ns) {
+                            atomicExch(p.status, 1);
+                            misc[1] = 1;
+                            break;
+                        }
+                    }
+                    __nanosleep(32);
+                }
+            }
+            __syncthreads();
+            if (misc[1]) return;  // watchdog: give up (host reports ACSFIT_E_TIMEOUT)
+            if (misc[2]) {
+                if (tid == 0) st_release(p.progress + stage, p.num_tiles);
+                return;
+            }
+        }
+
+        // ---- load the tile: compact the alive pods' rows into shared memory ----------------
+        const int64_t j = (int64_t)tile * kTile + tid;
+        const unsigned word = (j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
+        const bool is_alive = (word >> lane) & 1u;
+        if (lane == 0) {
+            wcount[warp] = __popc(word);
+            alive_w[warp] = word;
+        }
+        if (tid < kTile / 32) hitmask[tid] = 0;
+        __syncthreads();
+        unsigned base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kTile / 32; ++w) {
+            const unsigned c = wcount[w];
+            base += (w < warp) ? c : 0u;
+            total += c;
+        }
+        if (total == 0) {  // nothing alive: forward the tile untouched
+            if (tid == 0) st_release(p.progress + stage, tile + 1);
+            __syncthreads();  // wcount / alive_w are rewritten by the next iteration
+            continue;         // uniform: every thread sees the same total
+        }
+        if (is_alive) {
+            const unsigned pos = base + __popc(word & ((1u << lane) - 1u));
+            int64_t row = p.pod_idx ? (int64_t)__ldg(p.pod_idx + j) : j;
+            if (p.row_map) row = (int64_t)__ldg(p.row_map + row);
+            const double *src = p.req + (size_t)row * D;
+            double *dst = rows + (size_t)pos * D;
+#pragma unroll
+            for (int d = 0; d < D; d += 2)
+                *reinterpret_cast<double2 *>(dst + d) = __ldg(reinterpret_cast<const double2 *>(src + d));
+            slot_of[pos] = (unsigned short)tid;
+            cand[pos] = kNoCand;
+        }
+        __syncthreads();
+
+        // ---- scan: every (alive pod, stage node) pair under the tile-start thresholds -------
+        {
+            double t[K][D];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int d = 0; d < D; ++d) t[k][d] = thr_s[(size_t)d * Tn + slot + k * NS];
+            for (unsigned q = group; q < total; q += PG) {
+                double r[D];
+                load_row<D>(r, rows + (size_t)q * D);
+                unsigned best = kNoCand;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    bool ok = true;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) ok = ok && (r[d] <= t[k][d]);
+                    if (ok) best = (unsigned)(slot + k * NS);
+                }
+                if (best != kNoCand) {
+                    atomicMin(&cand[q], best);
+                    atomicOr(&hitmask[q >> 5], 1u << (q & 31));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- resolve hits strictly in pod order (warp 0), against the LIVE thresholds -------
+        if (warp == 0) {
+            int n_placed = 0;  // (lane 0)
+            for (int w = 0; w < kTile / 32; ++w) {
+                unsigned bits = hitmask[w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const unsigned q = (unsigned)(w * 32 + b);
+                    double r[D];
+                    load_row<D>(r, rows + (size_t)q * D);
+                    int found = -1;
+                    // nodes before cand[q] did not fit at tile start, hence not now either
+                    for (int nb = (int)(cand[q] & ~31u); nb < n_valid; nb += 32) {
+                        const int n = nb + lane;
+                        bool ok = n < n_valid;
+                        if (ok) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) ok = ok && (r[d] <= thr_s[(size_t)d * Tn + n]);
+                        }
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                        if (m) { found = nb + __ffs(m) - 1; break; }
+                    }
+                    if (found >= 0) {
+                        const int64_t gn = stage_lo + found;
+                        if (BINS) {
+                            // bins[i] = bins[i] - pod.resources (scaler.py:140 / :145-146)
+                            if (lane < D) {
+                                double *tp = thr_s + (size_t)lane * Tn + found;
+                                *tp = __dsub_rn(*tp, rows[(size_t)q * D + lane]);
+                            }
+                            if (lane == 0) {
+                                const unsigned ob = opened[found >> 5];
+                                const bool was_open = (ob >> (found & 31)) & 1u;
+                                opened[found >> 5] = ob | (1u << (found & 31));
+                                // credited tests: bins before it, plus itself when it already existed
+                                my_evals += (unsigned long long)(gn - 0) + (was_open ? 1ull : 0ull);
+                            }
+                        } else {
+                            // used_capacity += pod.resources (kube.py:171), then the new threshold
+                            if (lane < D) {
+                                double *up = p.used + (size_t)gn * D + lane;
+                                const double u = __dadd_rn(*up, rows[(size_t)q * D + lane]);
+                                *up = u;
+                                thr_s[(size_t)lane * Tn + found] =
+                                    node_threshold(p.cap_type[(size_t)p.node_type[gn] * D + lane], u);
+                            }
+                        }
+                        if (lane == 0) {
+                            const unsigned s = slot_of[q];
+                            p.placed[(int64_t)tile * kTile + s] = (int32_t)gn;
+                            alive_w[s >> 5] &= ~(1u << (s & 31));
+                            ++n_placed;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // publish the surviving pods of the tile
+            forwarded += (long long)total - n_placed;
+            __syncwarp();
+            if (lane < kTile / 32) {
+                const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
+                if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(p.progress + stage, tile + 1);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (BINS && my_evals) atomicAdd(p.evals, my_evals);
+        if (forwarded == 0) atomicExch(p.drained, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+
+// K0: capacity.is_possible over the pools (capacity.py:24-32): literal (unit - req) >= 0
+__global__ void feasible_mask_kernel(const double *__restrict__ req, int64_t P, int D,
+                                     const double *__restrict__ unit, int T,
+                                     uint8_t *__restrict__ out_mask, unsigned long long *out_evals)
+{
+    extern __shared__ double unit_s[];
+    for (int i = threadIdx.x; i < T * D; i += blockDim.x) unit_s[i] = unit[i];
+    __syncthreads();
+    unsigned long long evals = 0;
+    for (int64_t pidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pidx < P;
+         pidx += (int64_t)gridDim.x * blockDim.x) {
+        const double *r = req + (size_t)pidx * D;
+        uint8_t ok = 0;
+        for (int t = 0; t < T && !ok; ++t) {
+            ++evals;
+            bool all = true;
+            for (int d = 0; d < D; ++d) all = all && fits_bin(unit_s[t * D + d], r[d]);
+            ok = all ? 1 : 0;
+        }
+        out_mask[pidx] = ok;
+    }
+    if (out_evals) {
+        for (int o = 16; o > 0; o >>= 1) evals += __shfl_down_sync(0xFFFFFFFFu, evals, o);
+        if ((threadIdx.x & 31) == 0 && evals) atomicAdd(out_evals, evals);
+    }
+}
+
+// pool gate of fulfill_pending (scaler.py:134) over the still-unaccounted pods
+__global__ void eligible_kernel(const double *__restrict__ req, const int32_t *__restrict__ row_map,
+                                int64_t P, int D, const double *__restrict__ unit /*D, device*/,
+                                const int32_t *__restrict__ acc_pool, uint8_t *__restrict__ out_flag)
+{
+    for (int64_t pidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pidx < P;
+         pidx += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t f = 0;
+        if (acc_pool[pidx] < 0) {
+            const double *r = req + (size_t)(row_map ? row_map[pidx] : pidx) * D;
+            bool all = true;
+            for (int d = 0; d < D; ++d) all = all && fits_bin(unit[d], r[d]);
+            f = all ? 1 : 0;
+        }
+        out_flag[pidx] = f;
+    }
+}
+
+// K1: ordered occupancy sum per node (cluster.py:165-168), one thread per node
+__global__ void occupancy_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ run_idx,
+                                 const double *__restrict__ req_run, int64_t N, int D,
+                                 double *__restrict__ used)
+{
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
+         n += (int64_t)gridDim.x * blockDim.x) {
+        double acc[kMaxDims];
+        for (int d = 0; d < D; ++d) acc[d] = used[(size_t)n * D + d];
+        for (int64_t k = row_ptr[n]; k < row_ptr[n + 1]; ++k) {
+            const double *r = req_run + (size_t)run_idx[k] * D;
+            for (int d = 0; d < D; ++d) acc[d] = __dadd_rn(acc[d], r[d]);
+        }
+        for (int d = 0; d < D; ++d) used[(size_t)n * D + d] = acc[d];
+    }
+}
+
+}  // namespace acsfit

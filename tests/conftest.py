@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    """the plain-C oracle (TEST INFRASTRUCTURE): built on demand with gcc."""
+    import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """the product engine on cuda:0; GPU tests only."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from kubernetes_acs_engine_autoscaler_b200 import build as acs_build
+    acs_build.build()
+    from kubernetes_acs_engine_autoscaler_b200.engine import Engine
+    eng = Engine(0, watchdog_ms=15000)
+    yield eng
+    eng.close()
