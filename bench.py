@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- pod-fit decisions/s of the autoscaler tick on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|small]
+
+A "step" is one whole tick of the hot path over one synthetic snapshot
+(BASELINE.json configs[1] = 100k pending pods x 10k nodes x 4 dims x 1 pool):
+    get_pods_to_schedule (K0) + get_pending_pods (first-fit pipeline over nodes)
+    + fulfill_pending (first-fit pipeline over bins, pool arithmetic) + maintain (idle scan, actions).
+`value` = decisions / s with the snapshot resident in HBM; `e2e` = the same through the host-buffer
+plugin call (pinned host arrays, H2D + D2H inside the timed region).  A *decision* is one
+evaluation the reference itself performs of KubeNode.can_fit (kube.py:173) or of a
+`(x - pod.resources).possible` pool/bin test (scaler.py:134,139, capacity.py:30); the count is
+checked against the oracle's count in the parity tests.
+
+N > 1 (torchrun, one rank per GPU, NCCL): weak scaling, see run_ours().
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (P, N, D, T)
+    "small": (20000, 2000, 4, 1),
+    "c2": (100000, 10000, 4, 1),      # BASELINE.json configs[1] -- the metric's config
+    "c3": (1000000, 100000, 8, 8),    # configs[2]
+}
+METRIC = "pod-fit decisions/sec"
+UNIT = "decisions/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def algorithmic_bytes(decisions, P, N, D):
+    """8*D bytes per decision (the node / bin row the reference touches) plus the
+    compulsory P*(8D+4) + N*(16D+4) once per tick."""
+    return decisions * 8 * D + P * (8 * D + 4) + N * (16 * D + 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the plain-C oracle (the Python reference cannot travel)
+# ---------------------------------------------------------------------------------------------
+def oracle_tick(oracle, c, used):
+    mask, ev0 = oracle.feasible_mask(c["req"], c["unit_all"])
+    feas = c["req"][mask.astype(bool)]
+    placed, ev1 = oracle.first_fit_nodes(feas, c["cap_type"], c["node_type"], used)
+    pend = feas[placed < 0]
+    ev2 = 0
+    if len(pend):
+        r = oracle.fulfill_pending(pend, len(pend), c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                                   c["pool_ignored"], c["over_provision"])
+        ev2 = r["evals"]
+    st = oracle.node_states(c["row_ptr"], c["run_idx"], c["req_run"], c["flags_run"], c["cap_type"], c["node_type"],
+                            c["node_flags"], c["node_age"], len(feas) > 0, [1800])[0]
+    budget = c["pool_actual"].astype(np.int64) - 1
+    oracle.maintain_actions(st, c["node_pool"], budget, np.ones(c["T"], np.uint8), True)
+    return ev0 + ev1 + ev2
+
+
+def time_oracle(c, used0, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    times = []
+    decisions = 0
+    for i in range(warmup + steps):
+        used = used0.copy()
+        t0 = time.perf_counter()
+        decisions = oracle_tick(oracle, c, used)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return decisions, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference is pure
+    Python and lives only in the build container, so this arm times its plain-C restatement
+    (oracle/acsfit_oracle.c, pinned to the reference by tests/golden) -- a far FASTER baseline than
+    CPython (~0.13 M decisions/s) and single-threaded because first-fit is sequential."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn
+    P, N, D, T = CONFIGS[args.config]
+    c = syn.make_cluster(P, N, D, T, seed=20260921 + 2)
+    used0 = syn.initial_used(c)
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
+    decisions, times = time_oracle(c, used0, steps, warmup)
+    mean = float(np.mean(times))
+    value = decisions / mean
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d pending pods x %d nodes x %d dims x %d pool(s)" % (args.config, P, N, D, T),
+                   "decisions_per_step": int(decisions)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "full %s tick, %d timed step(s), plain-C oracle port, 1 of %d host cores"
+                                   % (args.config, steps, os.cpu_count())},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kubernetes_acs_engine_autoscaler_b200 import build as acs_build
+    from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn
+    from kubernetes_acs_engine_autoscaler_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pod-fit path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    acs_build.build()
+    eng = Engine(local_rank)
+    P, N, D, T = CONFIGS[args.config]
+    # weak scaling: every rank packs its own independent cluster shard of the configured size
+    c = syn.make_cluster(P, N, D, T, seed=20260921 + 2 + 1000 * rank)
+    used0_h = syn.initial_used(c)
+    i64, i32, f64, u8 = torch.int64, torch.int32, torch.float64, torch.uint8
+    d = {"req": eng.dev(c["req"], f64), "cap_type": eng.dev(c["cap_type"], f64),
+         "node_type": eng.dev(c["node_type"], i32), "used0": eng.dev(used0_h, f64),
+         "row_ptr": eng.dev(c["row_ptr"], i64), "run_idx": eng.dev(c["run_idx"], i32),
+         "req_run": eng.dev(c["req_run"], f64), "flags_run": eng.dev(c["flags_run"], u8),
+         "node_flags": eng.dev(c["node_flags"], u8), "node_age": eng.dev(c["node_age"], i64),
+         "node_pool": eng.dev(c["node_pool"], i32)}
+    used = torch.empty_like(d["used0"])
+    budget = c["pool_actual"].astype(np.int64) - 1
+    scalable = np.ones(T, np.uint8)
+    thr = np.array([1800], np.int64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)  # > 126 MB L2
+
+    def step_device():
+        used.copy_(d["used0"])
+        r = eng.scale_up(d["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                         c["pool_ignored"], c["over_provision"], d["cap_type"], d["node_type"], used)
+        st = eng.node_states(d["row_ptr"], d["run_idx"], d["req_run"], d["flags_run"], d["cap_type"], d["node_type"],
+                             d["node_flags"], d["node_age"], r["n_to_schedule"] > 0, thr)
+        eng.maintain_actions(st[0], d["node_pool"], budget, scalable, True)
+        return r
+
+    # pinned host copies for the end-to-end (plugin) path
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+    h = {k: pin(c[k]) for k in ("req", "cap_type", "node_type", "row_ptr", "run_idx", "req_run", "flags_run",
+                                "node_flags", "node_age", "node_pool")}
+    h_used0 = pin(used0_h)
+    h_used = pin(used0_h.copy())
+    h_out = {"feasible": pin(np.empty(P, np.uint8)), "placed": pin(np.empty(P, np.int32)),
+             "acc_pool": pin(np.empty(P, np.int32))}
+
+    def step_host():
+        np.copyto(h_used, h_used0)
+        r = eng.scale_up_host(h["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                              c["pool_ignored"], c["over_provision"], h["cap_type"], h["node_type"], h_used, out=h_out)
+        eng.maintain_host(h["row_ptr"], h["run_idx"], h["req_run"], h["flags_run"], h["cap_type"], h["node_type"],
+                          h["node_flags"], h["node_age"], h["node_pool"], r["n_to_schedule"] > 0, 1800, budget,
+                          scalable, True)
+        return r
+
+    R = c["req_run"].shape[0]
+    h2d = (c["req"].nbytes + c["cap_type"].nbytes + c["node_type"].nbytes + used0_h.nbytes  # scale_up_host
+           + c["row_ptr"].nbytes + c["run_idx"].nbytes + c["req_run"].nbytes + c["flags_run"].nbytes
+           + c["cap_type"].nbytes + c["node_type"].nbytes + c["node_flags"].nbytes + c["node_age"].nbytes
+           + c["node_pool"].nbytes + 8)
+    d2h = P * (1 + 4 + 4) + used0_h.nbytes + 2 * N
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        launches0 = eng.launch_count
+        res = None
+        for a, b in ev:
+            flush.fill_(1)  # evict L2 between timed iterations (inputs are smaller than L2)
+            torch.cuda.synchronize()
+            a.record()
+            res = step_fn()
+            b.record()
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        return res, total_ms, eng.launch_count - launches0
+
+    with ClockSampler(local_rank) as clocks:
+        res, dev_ms, launches = timed(step_device, args.steps, args.warmup)
+        res_h, host_ms, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
+    assert res_h["decisions"] == res["decisions"]
+
+    # roofline leg: the dominant kernel (first-fit pipeline) bracketed by CUDA events inside the library
+    eng.set_timing(True)
+    pipe_ms, pipe_dec, pipe_bytes = 0.0, 0, 0
+    for _ in range(max(1, min(args.steps, 5))):
+        flush.fill_(1)
+        used.copy_(d["used0"])
+        torch.cuda.synchronize()
+        r = eng.scale_up(d["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                         c["pool_ignored"], c["over_provision"], d["cap_type"], d["node_type"], used)
+        s = eng.pipeline_stats()
+        pipe_ms += s["ms"]
+        pipe_dec += s["decisions"]
+        pipe_bytes += algorithmic_bytes(s["decisions"], P, N + int(r["bins_opened"].sum()), D)
+    eng.set_timing(False)
+    stats = eng.pipeline_stats()
+
+    # max over ranks of the timed regions, sum of decisions
+    t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device=eng.device)
+    dec = torch.tensor([float(res["decisions"])], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dec, op=dist.ReduceOp.SUM)
+    dev_ms, host_ms = float(t[0]), float(t[1])
+    total_dec = float(dec[0])
+    value = total_dec * args.steps / (dev_ms * 1e-3)
+    e2e = total_dec * args.steps / (host_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = pipe_bytes / (pipe_ms * 1e-3) / 1e9 if pipe_ms > 0 else 0.0
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_pipeline_traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d pending pods x %d nodes x %d dims x %d pool(s) per GPU" % (args.config, P, N, D, T),
+                       "seed": 20260921 + 2, "decisions_per_step": int(total_dec),
+                       "pods_to_schedule": res["n_to_schedule"], "pending": res["n_pending"],
+                       "bins_opened": [int(x) for x in res["bins_opened"]],
+                       "l2": "flushed between timed iterations (256 MiB fill)",
+                       "parallelism": "1 rank" if world == 1 else "%d independent shards, all-reduce of counts" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "firstfit_pipeline_kernel (nodes + bins launches)",
+                         "kernel_ms_per_step": pipe_ms / max(1, min(args.steps, 5)),
+                         "kernel_decisions_per_s": pipe_dec / (pipe_ms * 1e-3) if pipe_ms > 0 else 0.0,
+                         "note": "algorithmic bytes per SURVEY 8(d) = 8*D per decision; node/bin rows are held in "
+                                 "shared memory/registers, so DRAM traffic is far below it and the kernel is "
+                                 "issue/latency-bound, not HBM-bound (DESIGN.md)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": host_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "pipeline": {"stages": stats["stages"], "tiles": stats["tiles"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            decisions, times = time_oracle(c, used0_h, 1, 0)
+            assert decisions == res["decisions"], (decisions, res["decisions"])
+            line["cpu_baseline"] = {"value": decisions / times[0], "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "the full %s tick once (%.1f s) on 1 of %d host cores, plain-C oracle port"
+                                              % (args.config, times[0], os.cpu_count())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,8 @@ SIGNATURES = {
     "acsfit_maintain_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
                                      c_i64, c_int, c_int, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "acsfit_launch_count": (c_u64, [c_vp]),
+    "acsfit_debug_profile": (c_int, [c_vp, c_int, c_vp, c_int, c_vp]),
+    "acsfit_debug_trace": (c_int, [c_vp, c_int, c_vp, c_int]),
     "acsfit_last_pipeline_stats": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 

@@ -35,6 +35,10 @@ struct acsfit_ctx {
     uint64_t launches = 0;
     // pipeline statistics of the last first-fit / bin-pack call
     bool timing = false;
+    unsigned long long *prof_dev = nullptr;  // developer probe buffer [kProfStages][8] + trace [kProfTiles][8]
+    int trace_stage = -1;
+    std::vector<unsigned long long> prof_host;
+    int prof_stages = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     uint64_t last_decisions = 0;
@@ -479,6 +483,42 @@ extern "C" acsfit_status acsfit_ctx_set_timing(acsfit_ctx *ctx, int enabled)
     return ACSFIT_OK;
 }
 
+// developer probe (not part of the stable ABI surface the host layer uses): per-stage clock64 phase
+// totals of the LAST pipeline launch. rows = stages, 8 columns.
+constexpr int kProfStages = 4096;
+constexpr int kProfTiles = 8192;
+extern "C" ACSFIT_API acsfit_status acsfit_debug_trace(acsfit_ctx *ctx, int stage, unsigned long long *out, int max_tiles)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    ctx->trace_stage = stage;
+    if (out && ctx->prof_dev) {
+        const int n = std::min(max_tiles, kProfTiles);
+        CUDA_TRY(cudaMemcpy(out, ctx->prof_dev + (size_t)kProfStages * 8, sizeof(unsigned long long) * n * 8,
+                            cudaMemcpyDeviceToHost));
+    }
+    return ACSFIT_OK;
+}
+extern "C" ACSFIT_API acsfit_status acsfit_debug_profile(acsfit_ctx *ctx, int enabled, unsigned long long *out,
+                                                         int max_stages, int *out_stages)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    if (enabled && !ctx->prof_dev) {
+        CUDA_TRY(cudaMalloc(&ctx->prof_dev, sizeof(unsigned long long) * (kProfStages + kProfTiles) * 8));
+    }
+    if (!enabled && ctx->prof_dev) {
+        cudaFree(ctx->prof_dev);
+        ctx->prof_dev = nullptr;
+    }
+    if (out && ctx->prof_dev && ctx->prof_stages > 0) {
+        const int n = std::min(std::min(ctx->prof_stages, max_stages), kProfStages);
+        CUDA_TRY(cudaMemcpy(out, ctx->prof_dev, sizeof(unsigned long long) * n * 8, cudaMemcpyDeviceToHost));
+        if (out_stages) *out_stages = n;
+    } else if (out_stages) {
+        *out_stages = 0;
+    }
+    return ACSFIT_OK;
+}
+
 extern "C" uint64_t acsfit_launch_count(const acsfit_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" acsfit_status acsfit_last_pipeline_stats(const acsfit_ctx *ctx, double *out_ms,
@@ -545,10 +585,10 @@ struct StagePlan {
 
 // cut `n_nodes` nodes into stages: the widest stage (<= 1024 nodes) that still gives at
 // least `min_stages` stages, so that every SM has a stage to run.
-static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages)
+static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D)
 {
     const int want = ctx->min_stages > 0 ? ctx->min_stages : 2 * ctx->num_sms;
-    int NS = kThreads;
+    int NS = max_stage_nodes(D) / kNodesPerThread;
     while (NS > 1 && (n_nodes + (int64_t)NS * kNodesPerThread - 1) / ((int64_t)NS * kNodesPerThread) < want) NS >>= 1;
     StagePlan p;
     p.NS = NS;
@@ -563,10 +603,18 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
 template <int D, bool BINS>
 static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
 {
-    const size_t smem = PipelineSmem<D>::bytes(pp.Tn);
+    const size_t smem = PipelineSmem<D, BINS>::bytes(pp.Tn);
     auto kern = firstfit_pipeline_kernel<D, BINS>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<stages, kThreads, smem, st>>>(pp);
+    PipelineParams q = pp;
+    q.prof = (ctx->prof_dev && stages <= kProfStages) ? ctx->prof_dev : nullptr;
+    if (q.prof) {
+        CUDA_TRY(cudaMemsetAsync(ctx->prof_dev, 0, sizeof(unsigned long long) * (kProfStages + kProfTiles) * 8, st));
+        ctx->prof_stages = stages;
+        q.trace = (ctx->trace_stage >= 0 && pp.num_tiles <= kProfTiles) ? ctx->prof_dev + (size_t)kProfStages * 8 : nullptr;
+        q.trace_stage = ctx->trace_stage;
+    }
+    kern<<<stages, kThreads, smem, st>>>(q);
     ++ctx->launches;
     CUDA_TRY(cudaGetLastError());
     return ACSFIT_OK;
@@ -606,7 +654,7 @@ static void reset_stats(acsfit_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 static size_t first_fit_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N)
 {
-    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0);
+    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0, 16);
     return 8192 + sizeof(uint32_t) * (size_t)((P + 31) / 32) + sizeof(int) * ((size_t)plan.stages + 8);
 }
 
@@ -622,7 +670,7 @@ static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const in
         CUDA_TRY(cudaGetLastError());
         return ACSFIT_OK;
     }
-    const StagePlan plan = plan_stages(ctx, N, 0);
+    const StagePlan plan = plan_stages(ctx, N, 0, D);
     const int64_t alive_words = (P + 31) / 32;
     TAKE(alive, uint32_t, alive_words);
     TAKE(sync_words, int, plan.stages + 8);
@@ -749,7 +797,7 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
             int32_t *list = list_a, *next = list_b;
             int64_t M = E, bin_base = 0;
             while (M > 0) {
-                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass);  // at most one bin per pod
+                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D);  // at most one bin per pod
                 CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
                 fill_alive_kernel<<<grid_for(ctx, (M + 31) / 32, 256), 256, 0, st>>>(alive, M);
                 fill_i32_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(placed, M, -1);

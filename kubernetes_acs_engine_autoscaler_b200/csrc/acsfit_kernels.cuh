@@ -35,8 +35,9 @@ namespace acsfit {
 constexpr int kTile = 256;         // pods per tile == threads per CTA
 constexpr int kThreads = 256;
 constexpr int kNodesPerThread = 4; // K: node rows a thread keeps in registers in the scan
-constexpr int kMaxStageNodes = kThreads * kNodesPerThread;  // 1024
+constexpr int kMaxStageNodes = kThreads * kNodesPerThread;  // 1024 (upper bound; see max_stage_nodes)
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
+constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
 constexpr int kMaxDims = 16;
 
 struct PipelineParams {
@@ -67,6 +68,9 @@ struct PipelineParams {
     int *drained;           // 1 int, zeroed: set by the first stage that forwards no pod at all
     unsigned long long *evals; // bins mode: credited bin tests (atomicAdd)
     unsigned long long watchdog_ns;
+    unsigned long long *prof;  // optional [stages][8] clock64 phase totals (developer probe), or nullptr
+    unsigned long long *trace; // optional [num_tiles][8] per-tile trace of stage `trace_stage`
+    int trace_stage;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p)
@@ -98,17 +102,24 @@ __device__ __forceinline__ void load_row(double (&r)[D], const double *src)
     }
 }
 
-// dynamic shared memory layout (doubles first for alignment)
-template <int D>
+// dynamic shared memory layout (doubles first for alignment).
+// nodes mode keeps three [D][Tn] arrays: scan thresholds, used (the mutable state) and capacity;
+// bins mode keeps one: the remaining capacity IS the threshold (finite values, Lemma B).
+template <int D, bool BINS>
 struct PipelineSmem {
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)D * Tn)  // rows, thr
-               + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ +
-                                     kMaxStageNodes / 32 /*opened*/ + 8 /*warp counts*/ + 4)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn)
+               + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + 8 /*opened*/ +
+                                     8 /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
+                                     7 * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
                + sizeof(unsigned short) * kTile /*slot_of*/;
     }
 };
+
+// widest stage the shared-memory budget allows (keeps >= 2 CTAs per SM resident)
+// one node per lane of the 8 resolver warps
+__host__ __device__ constexpr int max_stage_nodes(int D) { return D <= 8 ? 256 : 128; }
 
 template <int D, bool BINS>
 __global__ void __launch_bounds__(kThreads)
@@ -116,46 +127,62 @@ firstfit_pipeline_kernel(const PipelineParams p)
 {
     constexpr int K = kNodesPerThread;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *rows = reinterpret_cast<double *>(smem_raw);        // [kTile][D]
-    double *thr_s = rows + (size_t)kTile * D;                   // [D][Tn]
-    unsigned *cand = reinterpret_cast<unsigned *>(thr_s + (size_t)D * p.Tn);  // [kTile]
+    const int Tn = p.Tn;
+    double *rows = reinterpret_cast<double *>(smem_raw);        // [kTile][D]   compacted pod rows of the tile
+    double *state_s = rows + (size_t)kTile * D;                 // [D][Tn]      used (nodes) / remaining (bins)
+    double *thr_s = BINS ? state_s : state_s + (size_t)D * Tn;  // [D][Tn]      scan thresholds
+    double *cap_s = BINS ? state_s : thr_s + (size_t)D * Tn;    // [D][Tn]      capacity (nodes only)
+    unsigned *cand = reinterpret_cast<unsigned *>(state_s + (size_t)(BINS ? 1 : 3) * D * Tn);  // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
-    unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]
-    unsigned *opened = alive_w + kTile / 32;                    // [kMaxStageNodes/32]
-    unsigned *wcount = opened + kMaxStageNodes / 32;            // [8]
-    unsigned *misc = wcount + 8;                                // [4]: 0 = stage, 1 = abort flag, 2 = drained
-    unsigned short *slot_of = reinterpret_cast<unsigned short *>(misc + 4);  // [kTile]
+    unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
+    unsigned *opened = alive_w + kTile / 32;                    // [8] bins: bin already holds a pod (bit per node)
+    unsigned *dirty = opened + 8;                               // [8] nodes: threshold is stale (bit per node)
+    unsigned *wcount = dirty + 8;                               // [8]
+    unsigned *misc = wcount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
+    unsigned *hitlist = misc + 8;                               // [kTile+1] ordered hit entries (q+1), then kQueueEnd
+    unsigned *queue = hitlist + (kTile + 1);                    // [7][kTile+1] forward queue of warp w -> w+1
+    unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + 7 * (kTile + 1) + 1);  // [kTile]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int Tn = p.Tn;
 
     if (tid == 0) {
         misc[0] = (unsigned)atomicAdd(p.ticket, 1);
         misc[1] = 0;
         misc[2] = 0;
+        misc[3] = 0;
+        misc[4] = 0;
     }
     __syncthreads();
     const int stage = (int)misc[0];
     const int64_t stage_lo = p.node_lo + (int64_t)stage * Tn;   // global index of local node 0
     const int n_valid = (int)max((int64_t)0, min((int64_t)Tn, p.node_hi - stage_lo));
 
-    // ---- stage start: thresholds of this stage's nodes into shared memory ------------------
+    // ---- stage start: state + thresholds of this stage's nodes into shared memory ----------
     for (int i = tid; i < Tn * D; i += kThreads) {
         const int n = i / D, d = i - n * D;
-        double t = -1.0;  // padding nodes never fit
-        if (n < n_valid) {
-            if (BINS) {
-                t = p.unit[d];  // untouched bin: remaining == unit (scaler.py:145-146)
-            } else {
+        if (BINS) {
+            // untouched bin: remaining == unit (scaler.py:145-146); padding bins never fit
+            state_s[(size_t)d * Tn + n] = n < n_valid ? p.unit[d] : -1.0;
+        } else {
+            double u = 0.0, c = -1.0, t = -1.0;  // padding nodes never fit
+            if (n < n_valid) {
                 const int64_t gn = stage_lo + n;
-                t = node_threshold(p.cap_type[(size_t)p.node_type[gn] * D + d], p.used[(size_t)gn * D + d]);
+                u = p.used[(size_t)gn * D + d];
+                c = p.cap_type[(size_t)p.node_type[gn] * D + d];
+                t = node_threshold(c, u);
             }
+            state_s[(size_t)d * Tn + n] = u;
+            cap_s[(size_t)d * Tn + n] = c;
+            thr_s[(size_t)d * Tn + n] = t;
         }
-        thr_s[(size_t)d * Tn + n] = t;
     }
-    for (int i = tid; i < kMaxStageNodes / 32; i += kThreads) opened[i] = 0;
+    if (tid < 8) {
+        opened[tid] = 0;
+        dirty[tid] = 0;
+    }
+    for (int i = tid; i < 7 * (kTile + 1) + 1; i += kThreads) queue[i] = 0;
     __syncthreads();
 
     const int NS = p.NS;
@@ -164,9 +191,19 @@ firstfit_pipeline_kernel(const PipelineParams p)
     const int PG = kThreads / NS;
     unsigned long long my_evals = 0;
     long long forwarded = 0;  // (thread 0) pods this stage passed on to the next one
+    unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (thread 0) wait/load/scan/resolve/publish/refresh/hits/tiles
+    unsigned long long trace_prev[6] = {0, 0, 0, 0, 0, 0};
+    long long tp = 0;
+#define ACSFIT_PROF(i)                                   \
+    if (p.prof && tid == 0) {                            \
+        const long long now__ = clock64();               \
+        prof_acc[i] += (unsigned long long)(now__ - tp); \
+        tp = now__;                                      \
+    }
     const unsigned long long t_start = global_timer_ns();
 
     for (int tile = 0; tile < p.num_tiles; ++tile) {
+        if (p.prof && tid == 0) tp = clock64();
         // ---- wait until the previous stage has published this tile -------------------------
         if (stage > 0) {
             if (tid == 0) {
@@ -186,17 +223,15 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             break;
                         }
                     }
-                    __nanosleep(32);
+                    __nanosleep(20);
                 }
             }
             __syncthreads();
             if (misc[1]) return;  // watchdog: give up (host reports ACSFIT_E_TIMEOUT)
-            if (misc[2]) {
-                if (tid == 0) st_release(p.progress + stage, p.num_tiles);
-                return;
-            }
+            if (misc[2]) break;   // drained: nothing left to do (state write-back below)
         }
 
+        ACSFIT_PROF(0)
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
         const int64_t j = (int64_t)tile * kTile + tid;
         const unsigned word = (j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
@@ -216,7 +251,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         if (total == 0) {  // nothing alive: forward the tile untouched
             if (tid == 0) st_release(p.progress + stage, tile + 1);
-            __syncthreads();  // wcount / alive_w are rewritten by the next iteration
+            __syncthreads();  // wcount is rewritten by the next iteration
             continue;         // uniform: every thread sees the same total
         }
         if (is_alive) {
@@ -232,6 +267,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
             cand[pos] = kNoCand;
         }
         __syncthreads();
+        ACSFIT_PROF(1)
 
         // ---- scan: every (alive pod, stage node) pair under the tile-start thresholds -------
         {
@@ -258,81 +294,202 @@ firstfit_pipeline_kernel(const PipelineParams p)
             }
         }
         __syncthreads();
+        ACSFIT_PROF(2)
 
-        // ---- resolve hits strictly in pod order (warp 0), against the LIVE thresholds -------
-        if (warp == 0) {
-            int n_placed = 0;  // (lane 0)
+        // ---- resolve hits strictly in pod order: an intra-CTA systolic chain of warps -----------
+        // warp w owns nodes [32w, 32w+32) of the stage with their state in registers (lane <-> node)
+        // and evaluates the LITERAL reference predicate, so no threshold sits on this critical path.
+        // The ordered hit list enters warp 0; a warp either places the pod on its first fitting node
+        // or forwards it, in order, to warp w+1 through a shared-memory queue.  This is the reference's
+        // loop restricted to the stage's nodes, pipelined over the warps.
+        unsigned nh;
+        {
+            unsigned hb = 0, ht = 0;
+#pragma unroll
             for (int w = 0; w < kTile / 32; ++w) {
-                unsigned bits = hitmask[w];
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const unsigned q = (unsigned)(w * 32 + b);
-                    double r[D];
-                    load_row<D>(r, rows + (size_t)q * D);
+                const unsigned c = __popc(hitmask[w]);
+                hb += (w < warp) ? c : 0u;
+                ht += c;
+            }
+            nh = ht;
+            // queue entries: 0 = not written yet, q + 1 = compacted pod position q, kQueueEnd = end
+            const unsigned hw = hitmask[warp];
+            if ((hw >> lane) & 1u) hitlist[hb + __popc(hw & ((1u << lane) - 1u))] = (unsigned)tid + 1u;
+            if (tid == 0) hitlist[ht] = kQueueEnd;
+        }
+        __syncthreads();
+        if (nh > 0) {
+            const int n_warps = (n_valid + 31) >> 5;  // warps that own at least one real node
+            unsigned out = 0;
+            if (warp < n_warps) {
+                const int my_lo = warp << 5;
+                const int n = my_lo + lane;
+                const bool last = warp == n_warps - 1;
+                double S[D], C[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    S[d] = n < Tn ? state_s[(size_t)d * Tn + n] : (BINS ? -1.0 : 0.0);
+                    C[d] = (!BINS && n < Tn) ? cap_s[(size_t)d * Tn + n] : -1.0;
+                }
+                unsigned touched = 0;
+                unsigned was_opened = BINS ? opened[warp] : 0u;
+                const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
+                volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
+                unsigned head = 0;
+                int n_placed = 0;
+                // software pipeline: the entry, candidate and row of the NEXT hit are fetched while the
+                // current one is tested; only the node state S carries a dependency from hit to hit.
+                unsigned e = in_q[0];
+                for (unsigned spins = 0; e == 0; e = in_q[0])
+                    if (++spins > (1u << 27)) { atomicExch(p.status, 2); e = kQueueEnd; break; }
+                double r[D];
+                unsigned c = kNoCand, slot_cur = 0;
+                if (e != kQueueEnd) {
+                    load_row<D>(r, rows + (size_t)(e - 1) * D);
+                    c = cand[e - 1];
+                    slot_cur = slot_of[e - 1];
+                }
+                while (e != kQueueEnd) {
+                    // prefetch the next entry (may not be there yet)
+                    unsigned e_n = in_q[head + 1];
+                    double r_n[D];
+                    unsigned c_n = kNoCand, slot_n = 0;
+                    if (e_n != 0 && e_n != kQueueEnd) {
+                        load_row<D>(r_n, rows + (size_t)(e_n - 1) * D);
+                        c_n = cand[e_n - 1];
+                        slot_n = slot_of[e_n - 1];
+                    }
                     int found = -1;
                     // nodes before cand[q] did not fit at tile start, hence not now either
-                    for (int nb = (int)(cand[q] & ~31u); nb < n_valid; nb += 32) {
-                        const int n = nb + lane;
-                        bool ok = n < n_valid;
-                        if (ok) {
+                    if ((int)c < my_lo + 32) {
+                        bool ok = true;
 #pragma unroll
-                            for (int d = 0; d < D; ++d) ok = ok && (r[d] <= thr_s[(size_t)d * Tn + n]);
+                        for (int d = 0; d < D; ++d) {
+                            if (BINS) ok = ok & (__dsub_rn(S[d], r[d]) >= 0.0);               // scaler.py:139
+                            else ok = ok & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);  // kube.py:175
                         }
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                        if (m) { found = nb + __ffs(m) - 1; break; }
+                        if (m) {
+                            found = __ffs(m) - 1;
+                            if (lane == found) {
+#pragma unroll
+                                for (int d = 0; d < D; ++d)
+                                    S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
+                                                : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
+                            }
+                        }
                     }
                     if (found >= 0) {
-                        const int64_t gn = stage_lo + found;
+                        const int64_t gn = stage_lo + my_lo + found;
                         if (BINS) {
-                            // bins[i] = bins[i] - pod.resources (scaler.py:140 / :145-146)
-                            if (lane < D) {
-                                double *tp = thr_s + (size_t)lane * Tn + found;
-                                *tp = __dsub_rn(*tp, rows[(size_t)q * D + lane]);
-                            }
-                            if (lane == 0) {
-                                const unsigned ob = opened[found >> 5];
-                                const bool was_open = (ob >> (found & 31)) & 1u;
-                                opened[found >> 5] = ob | (1u << (found & 31));
-                                // credited tests: bins before it, plus itself when it already existed
-                                my_evals += (unsigned long long)(gn - 0) + (was_open ? 1ull : 0ull);
-                            }
-                        } else {
-                            // used_capacity += pod.resources (kube.py:171), then the new threshold
-                            if (lane < D) {
-                                double *up = p.used + (size_t)gn * D + lane;
-                                const double u = __dadd_rn(*up, rows[(size_t)q * D + lane]);
-                                *up = u;
-                                thr_s[(size_t)lane * Tn + found] =
-                                    node_threshold(p.cap_type[(size_t)p.node_type[gn] * D + lane], u);
-                            }
+                            // credited tests: every bin before it, plus itself when it already existed
+                            my_evals += (unsigned long long)gn + ((was_opened >> found) & 1u);
+                            was_opened |= 1u << found;
                         }
+                        touched |= 1u << found;
                         if (lane == 0) {
-                            const unsigned s = slot_of[q];
-                            p.placed[(int64_t)tile * kTile + s] = (int32_t)gn;
-                            alive_w[s >> 5] &= ~(1u << (s & 31));
-                            ++n_placed;
+                            p.placed[(int64_t)tile * kTile + slot_cur] = (int32_t)gn;
+                            atomicAnd(&alive_w[slot_cur >> 5], ~(1u << (slot_cur & 31)));
                         }
-                        __syncwarp();
+                        ++n_placed;
+                    } else if (!last) {
+                        if (lane == 0) out_q[out] = e;  // one word, self-validating: no fence needed
+                        ++out;
+                    }
+                    ++head;
+                    if (e_n == 0) {  // the producer had not written it yet: wait for it now
+                        for (unsigned spins = 0; (e_n = in_q[head]) == 0;)
+                            if (++spins > (1u << 27)) { atomicExch(p.status, 2); e_n = kQueueEnd; break; }
+                        if (e_n != kQueueEnd) {
+                            load_row<D>(r_n, rows + (size_t)(e_n - 1) * D);
+                            c_n = cand[e_n - 1];
+                            slot_n = slot_of[e_n - 1];
+                        }
+                    }
+                    e = e_n;
+                    c = c_n;
+                    slot_cur = slot_n;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) r[d] = r_n[d];
+                }
+                if (!last && lane == 0) out_q[out] = kQueueEnd;
+                if (lane == 0 && n_placed) atomicAdd(&misc[4], (unsigned)n_placed);
+                if (touched) {
+                    if (n < Tn) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) state_s[(size_t)d * Tn + n] = S[d];
+                    }
+                    if (lane == 0) {
+                        if (BINS) opened[warp] = was_opened;
+                        else dirty[warp] = touched;
                     }
                 }
             }
-            // publish the surviving pods of the tile
-            forwarded += (long long)total - n_placed;
-            __syncwarp();
+            __syncthreads();
+            // wipe the queue entries this warp wrote so that the next tile starts from "not written"
+            if (warp < n_warps - 1) {
+                unsigned *out_q = queue + (size_t)warp * (kTile + 1);
+                for (unsigned i = lane; i <= out; i += 32) out_q[i] = 0;
+            }
+        }
+        ACSFIT_PROF(3)
+        if (p.prof && tid == 0) { prof_acc[6] += nh; prof_acc[7] += 1; }
+        // ---- publish the surviving pods of the tile --------------------------------------------
+        if (warp == 0) {
+            const unsigned n_placed_tile = misc[4];
+            forwarded += (long long)total - (long long)n_placed_tile;
             if (lane < kTile / 32) {
                 const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
-                if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
+                if (wj * 32 < p.M && n_placed_tile) __stcg(p.alive + wj, alive_w[lane]);
             }
             __threadfence();
             __syncwarp();
-            if (lane == 0) st_release(p.progress + stage, tile + 1);
+            if (lane == 0) {
+                st_release(p.progress + stage, tile + 1);
+                misc[3] = n_placed_tile ? 1u : 0u;
+                misc[4] = 0;
+            }
         }
         __syncthreads();
+        ACSFIT_PROF(4)
+
+        // ---- nodes: refresh the scan thresholds of the nodes that took a pod (all threads) ----
+        if (!BINS && misc[3]) {
+            for (int i = tid; i < Tn * D; i += kThreads) {
+                const int d = i / Tn, n = i - d * Tn;
+                if ((dirty[n >> 5] >> (n & 31)) & 1u)
+                    thr_s[i] = node_threshold(cap_s[i], state_s[i]);
+            }
+            __syncthreads();
+            if (tid < 8) dirty[tid] = 0;
+            if (tid == 0) misc[3] = 0;
+            __syncthreads();
+        }
+        ACSFIT_PROF(5)
+        if (p.prof && p.trace && tid == 0 && stage == p.trace_stage) {
+            for (int i = 0; i < 6; ++i) {
+                p.trace[(size_t)tile * 8 + i] = prof_acc[i] - trace_prev[i];
+                trace_prev[i] = prof_acc[i];
+            }
+            p.trace[(size_t)tile * 8 + 6] = nh;
+            p.trace[(size_t)tile * 8 + 7] = total;
+        }
     }
+#undef ACSFIT_PROF
+    // ---- stage end: write the mutated node state back -------------------------------------
+    if (!BINS) {
+        for (int i = tid; i < Tn * D; i += kThreads) {
+            const int n = i / D, d = i - n * D;
+            if (n < n_valid) p.used[(size_t)(stage_lo + n) * D + d] = state_s[(size_t)d * Tn + n];
+        }
+    }
+    if (BINS && lane == 0 && my_evals) atomicAdd(p.evals, my_evals);  // every warp credits its own placements
     if (tid == 0) {
-        if (BINS && my_evals) atomicAdd(p.evals, my_evals);
+        if (misc[2]) st_release(p.progress + stage, p.num_tiles);
         if (forwarded == 0) atomicExch(p.drained, 1);
+        if (p.prof) {
+            for (int i = 0; i < 8; ++i) p.prof[(size_t)stage * 8 + i] = prof_acc[i];
+        }
     }
 }
 

@@ -103,6 +103,21 @@ class Engine(object):
                                                          ctypes.byref(stages), ctypes.byref(tiles)))
         return {"ms": ms.value, "decisions": dec.value, "stages": stages.value, "tiles": tiles.value}
 
+    def debug_profile(self, enabled=True):
+        """developer probe: per-stage clock64 totals [stages, 8] of the last pipeline launch
+        (wait, load, scan, resolve, publish, refresh, hits, tiles)."""
+        out = np.zeros((4096, 8), dtype=np.uint64)
+        n = ctypes.c_int(0)
+        self._check(self._lib.acsfit_debug_profile(self._ctx, 1 if enabled else 0, _ptr(out), 4096,
+                                                   ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+        return out[:n.value]
+
+    def debug_trace(self, stage, tiles=8192):
+        """developer probe: select the stage to trace / fetch its per-tile trace [tiles, 8]."""
+        out = np.zeros((tiles, 8), dtype=np.uint64)
+        self._check(self._lib.acsfit_debug_trace(self._ctx, int(stage), _ptr(out), tiles))
+        return out
+
     # ------------------------------------------------------------------ device entry points
     def feasible_mask(self, req, unit):
         """capacity.is_possible over all pools (capacity.py:24-32). req [P,D], unit [T,D] device."""
