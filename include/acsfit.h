@@ -257,6 +257,14 @@ ACSFIT_API uint64_t acsfit_launch_count(const acsfit_ctx *ctx);
 ACSFIT_API acsfit_status acsfit_last_pipeline_stats(const acsfit_ctx *ctx, double *out_ms,
                                          uint64_t *out_decisions, int *out_stages, int *out_tiles);
 
+/* developer probes (tools/perf_probe.py): per-stage clock64 phase totals [stages][8] of the last
+ * pipeline launch (wait, load, scan, resolve, publish, refresh, hits, tiles) and a per-tile trace
+ * [tiles][8] of one chosen stage.  Enabling them adds a clock read per phase on thread 0. */
+ACSFIT_API acsfit_status acsfit_debug_profile(acsfit_ctx *ctx, int enabled, unsigned long long *out,
+                                              int max_stages, int *out_stages);
+ACSFIT_API acsfit_status acsfit_debug_trace(acsfit_ctx *ctx, int stage, unsigned long long *out,
+                                            int max_tiles);
+
 #ifdef __cplusplus
 }
 #endif

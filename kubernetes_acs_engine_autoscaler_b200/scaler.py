@@ -1,0 +1,108 @@
+"""Scaling policy (mirror of reference autoscaler/scaler.py): fulfill_pending and get_node_state.
+
+The packing / classification arithmetic runs in libacsfit.so (first-fit pipeline over bins,
+idle scan); this class keeps the reference's surface, log lines and error behaviour.
+"""
+import logging
+
+import numpy as np
+
+from . import capacity
+from . import snapshot
+
+logger = logging.getLogger('autoscaler.scaler')
+
+
+class ClusterNodeState(object):
+    INSTANCE_TERMINATED = 'instance-terminated'
+    POD_PENDING = 'pod-pending'
+    GRACE_PERIOD = 'grace-period'
+    SPARE_AGENT = 'spare-agent'
+    IDLE_SCHEDULABLE = 'idle-schedulable'
+    IDLE_UNSCHEDULABLE = 'idle-unschedulable'
+    BUSY_UNSCHEDULABLE = 'busy-unschedulable'
+    BUSY = 'busy'
+    UNDER_UTILIZED_DRAINABLE = 'under-utilized-drainable'
+    UNDER_UTILIZED_UNDRAINABLE = 'under-utilized-undrainable'
+
+
+# include/acsfit.h ACSFIT_ST_* code -> state string (listing order of scaler.py:19-29)
+STATE_NAMES = [
+    ClusterNodeState.INSTANCE_TERMINATED, ClusterNodeState.POD_PENDING, ClusterNodeState.GRACE_PERIOD,
+    ClusterNodeState.SPARE_AGENT, ClusterNodeState.IDLE_SCHEDULABLE, ClusterNodeState.IDLE_UNSCHEDULABLE,
+    ClusterNodeState.BUSY_UNSCHEDULABLE, ClusterNodeState.BUSY, ClusterNodeState.UNDER_UTILIZED_DRAINABLE,
+    ClusterNodeState.UNDER_UTILIZED_UNDRAINABLE,
+]
+# per-pod log lines are only emitted up to this many pods (O(P) strings)
+LOG_DETAIL_LIMIT = 20000
+
+
+class Scaler(object):
+    # a node is under-utilised when its busy pods use <= 30 % of every capacity dimension
+    UTIL_THRESHOLD = 0.3
+
+    def __init__(self, resource_group, nodes, over_provision, spare_count, idle_threshold, dry_run,
+                 deployments, notifier):
+        self.resource_group_name = resource_group
+        self.over_provision = over_provision
+        self.spare_count = spare_count
+        self.idle_threshold = idle_threshold
+        self.dry_run = dry_run
+        self.deployments = deployments
+        self.notifier = notifier
+        self.max_agent_pool_size = 100
+        self.agent_pools = None
+        self.scalable_pools = None
+        self.ignored_pool_names = {}
+
+    def get_agent_pools(self, nodes):
+        raise NotImplementedError()
+
+    def scale_pools(self, pool_sizes):
+        raise NotImplementedError()
+
+    def get_node_state(self, node, node_pods, pods_to_schedule):
+        """ClusterNodeState of one node (scaler.py:61-114): a one-node launch of the idle scan.
+        EngineScaler.maintain classifies all nodes in a single launch instead."""
+        code = snapshot.node_states([node], [list(node_pods)], bool(pods_to_schedule), self.idle_threshold)
+        return STATE_NAMES[int(code.cpu().numpy()[0])]
+
+    def fulfill_pending(self, pods):
+        """number of new VMs per pool needed for the pending pods (scaler.py:117-184)."""
+        logger.info("====Scaling for %s pods ====", len(pods))
+        # the reference keys its bookkeeping by pod (hash = uid): duplicates collapse onto their first
+        # occurrence, but num_unaccounted starts at len(pods) (scaler.py:119-120)
+        unique = list(dict((p, False) for p in pods).keys())
+        ordered_pools = capacity.order_by_cost_asc(self.agent_pools)
+        res = snapshot.fulfill(unique, len(pods), ordered_pools, self.ignored_pool_names, self.over_provision)
+
+        new_pool_sizes, current_pool_sizes = {}, {}
+        unaccounted = len(pods)
+        acc = res["acc_pool"]
+        for t, pool in enumerate(ordered_pools):
+            current_pool_sizes[pool.name] = pool.actual_capacity
+            new_pool_sizes[pool.name] = int(res["new_size"][t])
+            needed = int(res["units_needed"][t])
+            if needed < 0:  # pool skipped (ignored, or nothing left to place)  scaler.py:128-129
+                continue
+            requested = new_pool_sizes[pool.name] - pool.actual_capacity
+            logger.debug("units_needed: %s", needed)
+            logger.debug("units_requested: %s", requested)
+            logger.debug('{} actual capacity: {} , units requested: {}'.format(
+                pool.name, pool.actual_capacity, requested))
+            logger.info("New capacity requested for pool {}: {} agents (current capacity: {} agents)".format(
+                pool.name, new_pool_sizes[pool.name], pool.actual_capacity))
+            unaccounted -= int(np.count_nonzero(acc == t))
+            logger.debug("remaining pending: %s", unaccounted)
+        assert unaccounted == res["num_unaccounted"]
+
+        if unaccounted:
+            logger.warning('Failed to scale sufficiently.')
+            # the reference evaluates `self.notifier.notify_failed_to_scale(selectors_hash, pods)` here,
+            # where `selectors_hash` is an undefined name (scaler.py:181): AttributeError when the
+            # notifier lacks the method, NameError otherwise -- and scale_pools is never reached.
+            self.notifier.notify_failed_to_scale
+            raise NameError("name 'selectors_hash' is not defined")
+        self.scale_pools(new_pool_sizes)
+        if self.notifier:
+            self.notifier.notify_scale(new_pool_sizes, pods, current_pool_sizes)
