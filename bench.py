@@ -168,18 +168,18 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from kubernetes_acs_engine_autoscaler_b200 import build as acs_build
+    from kubernetes_acs_engine_autoscaler_b200 import distributed as acs_dist
     from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn
     from kubernetes_acs_engine_autoscaler_b200.engine import Engine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the pod-fit path has no CPU fallback")
+    rank, world, local_rank = acs_dist.env_rank()
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    acs_build.build()
+    acs_dist.init("nccl")
+    if rank == 0:
+        acs_build.build()
+    acs_dist.barrier()
     eng = Engine(local_rank)
     P, N, D, T = CONFIGS[args.config]
     # weak scaling: every rank packs its own independent cluster shard of the configured size
@@ -202,6 +202,8 @@ def run_ours(args):
         used.copy_(d["used0"])
         r = eng.scale_up(d["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
                          c["pool_ignored"], c["over_provision"], d["cap_type"], d["node_type"], used)
+        if world > 1:  # the one collective of the path: fleet totals of the per-pool integer counts
+            r["fleet"] = acs_dist.fleet_scale_up(r, c["pool_actual"])
         st = eng.node_states(d["row_ptr"], d["run_idx"], d["req_run"], d["flags_run"], d["cap_type"], d["node_type"],
                              d["node_flags"], d["node_age"], r["n_to_schedule"] > 0, thr)
         eng.maintain_actions(st[0], d["node_pool"], budget, scalable, True)
@@ -222,6 +224,8 @@ def run_ours(args):
         np.copyto(h_used, h_used0)
         r = eng.scale_up_host(h["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
                               c["pool_ignored"], c["over_provision"], h["cap_type"], h["node_type"], h_used, out=h_out)
+        if world > 1:
+            r["fleet"] = acs_dist.fleet_scale_up(r, c["pool_actual"])
         eng.maintain_host(h["row_ptr"], h["run_idx"], h["req_run"], h["flags_run"], h["cap_type"], h["node_type"],
                           h["node_flags"], h["node_age"], h["node_pool"], r["n_to_schedule"] > 0, 1800, budget,
                           scalable, True)
@@ -330,8 +334,7 @@ def run_ours(args):
                                     "sample": "the full %s tick once (%.1f s) on 1 of %d host cores, plain-C oracle port"
                                               % (args.config, times[0], os.cpu_count())}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    acs_dist.shutdown()
 
 
 def main():
