@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -23,8 +24,9 @@ using namespace acsfit;
 struct acsfit_ctx {
     int device = 0;
     int num_sms = 0;
-    int min_stages = 0;       // 0 = 2 x SMs
+    int min_stages = 0;       // 0 = number of SMs
     int watchdog_ms = 20000;
+    int smem_floor_kb = 0;    // >0: request at least this much dynamic smem per stage CTA (limits CTAs per SM)
     char err[512] = {0};
     // grow-only device arena, bump-allocated per API call
     unsigned char *arena = nullptr;
@@ -452,6 +454,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
         delete ctx;
         return ACSFIT_E_CUDA;
     }
+    if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
     *out_ctx = ctx;
     return ACSFIT_OK;
 }
@@ -587,7 +590,7 @@ struct StagePlan {
 // least `min_stages` stages, so that every SM has a stage to run.
 static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D)
 {
-    const int want = ctx->min_stages > 0 ? ctx->min_stages : 2 * ctx->num_sms;
+    const int want = ctx->min_stages > 0 ? ctx->min_stages : ctx->num_sms;  // one stage per SM measured best
     int NS = max_stage_nodes(D) / kNodesPerThread;
     while (NS > 1 && (n_nodes + (int64_t)NS * kNodesPerThread - 1) / ((int64_t)NS * kNodesPerThread) < want) NS >>= 1;
     StagePlan p;
@@ -603,7 +606,8 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
 template <int D, bool BINS>
 static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
 {
-    const size_t smem = PipelineSmem<D, BINS>::bytes(pp.Tn);
+    size_t smem = PipelineSmem<D, BINS>::bytes(pp.Tn);
+    if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
     auto kern = firstfit_pipeline_kernel<D, BINS>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PipelineParams q = pp;

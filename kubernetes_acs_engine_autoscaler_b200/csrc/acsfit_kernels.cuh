@@ -38,6 +38,7 @@ constexpr int kNodesPerThread = 4; // K: node rows a thread keeps in registers i
 constexpr int kMaxStageNodes = kThreads * kNodesPerThread;  // 1024 (upper bound; see max_stage_nodes)
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
+constexpr int kMinBatch = 8;  // entries a consumer warp waits for before it starts a batch
 constexpr int kMaxDims = 16;
 
 struct PipelineParams {
@@ -109,7 +110,7 @@ template <int D, bool BINS>
 struct PipelineSmem {
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)8 * 33 * D /*batch rows*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + 8 /*opened*/ +
                                      8 /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      7 * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
@@ -117,9 +118,20 @@ struct PipelineSmem {
     }
 };
 
-// widest stage the shared-memory budget allows (keeps >= 2 CTAs per SM resident)
 // one node per lane of the 8 resolver warps
 __host__ __device__ constexpr int max_stage_nodes(int D) { return D <= 8 ? 256 : 128; }
+
+// spin on a shared-memory queue word until the producer warp has written it (0 = not yet)
+__device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, int *status)
+{
+    unsigned e = *slot;
+    for (unsigned spins = 0; e == 0; e = *slot)
+        if (++spins > (1u << 27)) {  // never expected: refuse to hang the GPU
+            atomicExch(status, 2);
+            return kQueueEnd;
+        }
+    return e;
+}
 
 template <int D, bool BINS>
 __global__ void __launch_bounds__(kThreads)
@@ -132,7 +144,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
     double *state_s = rows + (size_t)kTile * D;                 // [D][Tn]      used (nodes) / remaining (bins)
     double *thr_s = BINS ? state_s : state_s + (size_t)D * Tn;  // [D][Tn]      scan thresholds
     double *cap_s = BINS ? state_s : thr_s + (size_t)D * Tn;    // [D][Tn]      capacity (nodes only)
-    unsigned *cand = reinterpret_cast<unsigned *>(state_s + (size_t)(BINS ? 1 : 3) * D * Tn);  // [kTile]
+    double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [8 warps][33][D] rows of a resolver batch (+1 padding row)
+    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)8 * 33 * D);  // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
     unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
     unsigned *opened = alive_w + kTile / 32;                    // [8] bins: bin already holds a pod (bit per node)
@@ -158,6 +171,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     const int stage = (int)misc[0];
     const int64_t stage_lo = p.node_lo + (int64_t)stage * Tn;   // global index of local node 0
     const int n_valid = (int)max((int64_t)0, min((int64_t)Tn, p.node_hi - stage_lo));
+    const int n_warps = (n_valid + 31) >> 5;                     // resolver warps that own a real node
 
     // ---- stage start: state + thresholds of this stage's nodes into shared memory ----------
     for (int i = tid; i < Tn * D; i += kThreads) {
@@ -182,7 +196,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
         opened[tid] = 0;
         dirty[tid] = 0;
     }
-    for (int i = tid; i < 7 * (kTile + 1) + 1; i += kThreads) queue[i] = 0;
+    for (int i = tid; i < 8 * (kTile + 1) + 1; i += kThreads) hitlist[i] = 0;  // hit list + the 7 queues
     __syncthreads();
 
     const int NS = p.NS;
@@ -190,7 +204,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     const int group = tid / NS;
     const int PG = kThreads / NS;
     unsigned long long my_evals = 0;
-    long long forwarded = 0;  // (thread 0) pods this stage passed on to the next one
+    long long forwarded = 0;  // (warp 0) pods this stage passed on to the next one
     unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (thread 0) wait/load/scan/resolve/publish/refresh/hits/tiles
     unsigned long long trace_prev[6] = {0, 0, 0, 0, 0, 0};
     long long tp = 0;
@@ -202,16 +216,35 @@ firstfit_pipeline_kernel(const PipelineParams p)
     }
     const unsigned long long t_start = global_timer_ns();
 
+    // the pod list is static, so the row of this thread's entry in the NEXT tile can be fetched from L2
+    // while the current tile is scanned; only the alive word has to wait for the upstream stage.
+    double pre[D];
+    auto prefetch_row = [&](int tile) {
+        const int64_t j = (int64_t)tile * kTile + tid;
+        if (tile < p.num_tiles && j < p.M) {
+            int64_t row = p.pod_idx ? (int64_t)__ldg(p.pod_idx + j) : j;
+            if (p.row_map) row = (int64_t)__ldg(p.row_map + row);
+            const double *src = p.req + (size_t)row * D;
+#pragma unroll
+            for (int d = 0; d < D; d += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2 *>(src + d));
+                pre[d] = v.x;
+                pre[d + 1] = v.y;
+            }
+        }
+    };
+    prefetch_row(0);
+
     for (int tile = 0; tile < p.num_tiles; ++tile) {
         if (p.prof && tid == 0) tp = clock64();
-        // ---- wait until the previous stage has published this tile -------------------------
+        // ---- wait until the previous stage has published this tile (warp 1 polls, so that warp 0
+        //      can still be publishing the previous tile) ---------------------------------------
         if (stage > 0) {
-            if (tid == 0) {
+            if (tid == 32) {
                 const int *flag = p.progress + (stage - 1);
                 unsigned spins = 0;
                 if (*(volatile int *)p.drained) {
-                    // an earlier stage finished with nothing left alive: every remaining tile is
-                    // empty, publish them all at once and leave
+                    // an earlier stage finished with nothing left alive: every remaining tile is empty
                     misc[2] = 1;
                 } else
                 while (ld_acquire(flag) <= tile) {
@@ -226,12 +259,12 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     __nanosleep(20);
                 }
             }
-            __syncthreads();
-            if (misc[1]) return;  // watchdog: give up (host reports ACSFIT_E_TIMEOUT)
-            if (misc[2]) break;   // drained: nothing left to do (state write-back below)
         }
-
+        __syncthreads();  // (S1) previous tile fully retired (publish included), poll result visible
+        if (misc[1]) return;  // watchdog: give up (host reports ACSFIT_E_TIMEOUT)
+        if (misc[2]) break;   // drained: nothing left to do (state write-back below)
         ACSFIT_PROF(0)
+
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
         const int64_t j = (int64_t)tile * kTile + tid;
         const unsigned word = (j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
@@ -240,7 +273,11 @@ firstfit_pipeline_kernel(const PipelineParams p)
             wcount[warp] = __popc(word);
             alive_w[warp] = word;
         }
-        if (tid < kTile / 32) hitmask[tid] = 0;
+        if (tid < kTile / 32) {
+            hitmask[tid] = 0;
+            dirty[tid] = 0;
+        }
+        if (tid == 0) misc[4] = 0;
         __syncthreads();
         unsigned base = 0, total = 0;
 #pragma unroll
@@ -251,45 +288,65 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         if (total == 0) {  // nothing alive: forward the tile untouched
             if (tid == 0) st_release(p.progress + stage, tile + 1);
-            __syncthreads();  // wcount is rewritten by the next iteration
-            continue;         // uniform: every thread sees the same total
+            prefetch_row(tile + 1);
+            continue;  // uniform: every thread sees the same total; (S1) protects the shared words
         }
         if (is_alive) {
             const unsigned pos = base + __popc(word & ((1u << lane) - 1u));
-            int64_t row = p.pod_idx ? (int64_t)__ldg(p.pod_idx + j) : j;
-            if (p.row_map) row = (int64_t)__ldg(p.row_map + row);
-            const double *src = p.req + (size_t)row * D;
             double *dst = rows + (size_t)pos * D;
 #pragma unroll
-            for (int d = 0; d < D; d += 2)
-                *reinterpret_cast<double2 *>(dst + d) = __ldg(reinterpret_cast<const double2 *>(src + d));
+            for (int d = 0; d < D; d += 2) *reinterpret_cast<double2 *>(dst + d) = make_double2(pre[d], pre[d + 1]);
             slot_of[pos] = (unsigned short)tid;
             cand[pos] = kNoCand;
         }
+        prefetch_row(tile + 1);
         __syncthreads();
         ACSFIT_PROF(1)
 
         // ---- scan: every (alive pod, stage node) pair under the tile-start thresholds -------
-        {
+        // bins: while the stage still owns an untouched bin every eligible pod fits it (scaler.py:134 is the
+        // same test), so every alive pod is a hit and the resolver starts it at the stage's first bin.
+        bool all_hit = false;
+        if (BINS) {
+            int n_open = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) n_open += __popc(opened[w]);
+            all_hit = n_open < n_valid;
+        }
+        if (all_hit) {
+            if (tid < total) cand[tid] = 0;
+            if (tid < kTile / 32) {
+                const int lo = tid * 32;
+                hitmask[tid] = (int)total >= lo + 32 ? 0xFFFFFFFFu : ((int)total > lo ? (1u << (total - lo)) - 1u : 0u);
+            }
+        } else {
             double t[K][D];
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int d = 0; d < D; ++d) t[k][d] = thr_s[(size_t)d * Tn + slot + k * NS];
-            for (unsigned q = group; q < total; q += PG) {
+            for (unsigned qb = 0; qb < total; qb += PG) {  // warp-uniform trip count (votes inside)
+                const unsigned q = qb + group;
+                const bool live = q < total;
                 double r[D];
-                load_row<D>(r, rows + (size_t)q * D);
+                load_row<D>(r, rows + (size_t)(live ? q : total - 1) * D);
                 unsigned best = kNoCand;
 #pragma unroll
                 for (int k = K - 1; k >= 0; --k) {
-                    bool ok = true;
+                    bool ok = live;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) ok = ok && (r[d] <= t[k][d]);
+                    for (int d = 0; d < D; ++d) ok = ok & (r[d] <= t[k][d]);
                     if (ok) best = (unsigned)(slot + k * NS);
                 }
-                if (best != kNoCand) {
-                    atomicMin(&cand[q], best);
-                    atomicOr(&hitmask[q >> 5], 1u << (q & 31));
+                // hits are rare: one vote, and only then a segmented min over the lanes that share q
+                // (NS consecutive lanes, or the whole warp when NS >= 32) before a single shared atomic
+                if (__any_sync(0xFFFFFFFFu, best != kNoCand)) {
+                    const int seg = NS < 32 ? NS : 32;
+                    for (int o = seg >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+                    if ((lane & (seg - 1)) == 0 && best != kNoCand) {
+                        atomicMin(&cand[q], best);
+                        atomicOr(&hitmask[q >> 5], 1u << (q & 31));
+                    }
                 }
             }
         }
@@ -300,8 +357,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
         // warp w owns nodes [32w, 32w+32) of the stage with their state in registers (lane <-> node)
         // and evaluates the LITERAL reference predicate, so no threshold sits on this critical path.
         // The ordered hit list enters warp 0; a warp either places the pod on its first fitting node
-        // or forwards it, in order, to warp w+1 through a shared-memory queue.  This is the reference's
-        // loop restricted to the stage's nodes, pipelined over the warps.
+        // or forwards it, in order, to warp w+1 through a shared-memory queue of self-validating words.
         unsigned nh;
         {
             unsigned hb = 0, ht = 0;
@@ -312,14 +368,15 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 ht += c;
             }
             nh = ht;
-            // queue entries: 0 = not written yet, q + 1 = compacted pod position q, kQueueEnd = end
-            const unsigned hw = hitmask[warp];
-            if ((hw >> lane) & 1u) hitlist[hb + __popc(hw & ((1u << lane) - 1u))] = (unsigned)tid + 1u;
-            if (tid == 0) hitlist[ht] = kQueueEnd;
+            if (nh > 0) {
+                // queue entries: 0 = not written yet, q + 1 = compacted pod position q, kQueueEnd = end
+                const unsigned hw = hitmask[warp];
+                if ((hw >> lane) & 1u) hitlist[hb + __popc(hw & ((1u << lane) - 1u))] = (unsigned)tid + 1u;
+                if (tid == 0) hitlist[ht] = kQueueEnd;
+            }
         }
-        __syncthreads();
         if (nh > 0) {
-            const int n_warps = (n_valid + 31) >> 5;  // warps that own at least one real node
+            __syncthreads();
             unsigned out = 0;
             if (warp < n_warps) {
                 const int my_lo = warp << 5;
@@ -331,97 +388,128 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     S[d] = n < Tn ? state_s[(size_t)d * Tn + n] : (BINS ? -1.0 : 0.0);
                     C[d] = (!BINS && n < Tn) ? cap_s[(size_t)d * Tn + n] : -1.0;
                 }
-                unsigned touched = 0;
-                unsigned was_opened = BINS ? opened[warp] : 0u;
+                // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
+                unsigned touched_or_open = BINS ? opened[warp] : 0u;
+                unsigned ev_local = 0;
                 const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
                 unsigned head = 0;
                 int n_placed = 0;
-                // software pipeline: the entry, candidate and row of the NEXT hit are fetched while the
-                // current one is tested; only the node state S carries a dependency from hit to hit.
-                unsigned e = in_q[0];
-                for (unsigned spins = 0; e == 0; e = in_q[0])
-                    if (++spins > (1u << 27)) { atomicExch(p.status, 2); e = kQueueEnd; break; }
-                double r[D];
-                unsigned c = kNoCand, slot_cur = 0;
-                if (e != kQueueEnd) {
-                    load_row<D>(r, rows + (size_t)(e - 1) * D);
-                    c = cand[e - 1];
-                    slot_cur = slot_of[e - 1];
-                }
-                while (e != kQueueEnd) {
-                    // prefetch the next entry (may not be there yet)
-                    unsigned e_n = in_q[head + 1];
-                    double r_n[D];
-                    unsigned c_n = kNoCand, slot_n = 0;
-                    if (e_n != 0 && e_n != kQueueEnd) {
-                        load_row<D>(r_n, rows + (size_t)(e_n - 1) * D);
-                        c_n = cand[e_n - 1];
-                        slot_n = slot_of[e_n - 1];
+                bool done = false;
+                const bool tracing = p.prof && p.trace && stage == p.trace_stage;
+                long long tw = 0, tb = 0, t_loop = 0, t_mark = tracing ? clock64() : 0;
+                unsigned n_batches = 0;
+                while (!done) {
+                    // a batch of up to 32 entries: lane i takes entry head+i with its candidate and slot;
+                    // only the node state S carries a dependency from one entry to the next.
+                    const unsigned idx = head + lane <= (unsigned)kTile ? head + lane : (unsigned)kTile;
+                    unsigned e, present;
+                    int nb;
+                    for (unsigned spins = 0;; ++spins) {
+                        e = in_q[idx];
+                        if (head + lane > (unsigned)kTile) e = 0;
+                        present = __ballot_sync(0xFFFFFFFFu, e != 0);
+                        nb = __ffs(~present) ? __ffs(~present) - 1 : 32;  // written entries form a prefix
+                        // a consumer warp takes entries in batches of >= kMinBatch (or up to the end marker):
+                        // one-entry batches would pay the batch set-up for every pod the producer forwards
+                        const bool has_end = __any_sync(0xFFFFFFFFu, lane < nb && e == kQueueEnd);
+                        if (has_end || nb >= kMinBatch) break;
+                        __nanosleep(64);  // do not hammer the shared-memory pipe the producer warp needs
+                        
+                        if (spins > (1u << 26)) {  // never expected: refuse to hang the GPU
+                            atomicExch(p.status, 2);
+                            e = lane == 0 ? kQueueEnd : 0u;
+                            present = 1u;
+                            nb = 1;
+                            break;
+                        }
                     }
-                    int found = -1;
+                    if (tracing) { const long long now = clock64(); tw += now - t_mark; t_mark = now; ++n_batches; }
+                    const unsigned endmask = __ballot_sync(0xFFFFFFFFu, lane < nb && e == kQueueEnd);
+                    const int n_ent = endmask ? __ffs(endmask) - 1 : nb;
+                    const bool mine = lane < n_ent;  // words after the end marker are stale: never touch them
+                    const unsigned q_l = mine ? e - 1 : 0;
+                    const unsigned c_l = mine ? cand[q_l] : kNoCand;
+                    const unsigned s_l = mine ? slot_of[q_l] : 0;
                     // nodes before cand[q] did not fit at tile start, hence not now either
-                    if ((int)c < my_lo + 32) {
+                    const unsigned testmask = __ballot_sync(0xFFFFFFFFu, mine && (int)c_l < my_lo + 32);
+                    int placed_here = -1;  // lane i: LOCAL node (of this warp) that took entry i of the batch
+                    // stage the batch's rows contiguously (lane i copies its own row) so that the loop below
+                    // reads entry k at a fixed stride and fetches entry k+1 while entry k is being tested.
+                    // An entry this warp need not test (its candidate lies in a later warp) is staged with
+                    // +inf in dimension 0: the same compare then fails on every lane, without a branch.
+                    double *brow = brows + (size_t)warp * 33 * D;
+                    if (mine) {
+                        double own[D];
+                        load_row<D>(own, rows + (size_t)q_l * D);
+                        if (!((testmask >> lane) & 1u)) own[0] = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+                        for (int d = 0; d < D; d += 2)
+                            *reinterpret_cast<double2 *>(brow + (size_t)lane * D + d) = make_double2(own[d], own[d + 1]);
+                    }
+                    __syncwarp();
+                    double r[D];
+                    load_row<D>(r, brow);
+                    const long long t_l0 = tracing ? clock64() : 0;
+                    unsigned took = 0;  // bit k: entry k of the batch was placed by this warp
+#pragma unroll 2
+                    for (int k = 0; k < n_ent; ++k) {
+                        double r_next[D];
+                        load_row<D>(r_next, brow + (size_t)(k + 1) * D);  // row 32 is padding
                         bool ok = true;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
-                            if (BINS) ok = ok & (__dsub_rn(S[d], r[d]) >= 0.0);               // scaler.py:139
+                            if (BINS) ok = ok & (r[d] <= S[d]);   // == (S - r >= 0) for finite values (scaler.py:139)
                             else ok = ok & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);  // kube.py:175
                         }
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                         if (m) {
-                            found = __ffs(m) - 1;
+                            const int found = __ffs(m) - 1;
                             if (lane == found) {
 #pragma unroll
                                 for (int d = 0; d < D; ++d)
                                     S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
                                                 : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
                             }
+                            // credited tests (bins): every bin before it, plus itself when it already existed;
+                            // the stage/warp base is added once per tile below
+                            ev_local += (unsigned)found + ((touched_or_open >> found) & 1u);
+                            touched_or_open |= 1u << found;
+                            placed_here = lane == k ? found : placed_here;
+                            took |= 1u << k;
+                        } else if (!last) {
+                            if (lane == k) out_q[out] = e;  // one word, self-validating: no fence needed
+                            ++out;
                         }
-                    }
-                    if (found >= 0) {
-                        const int64_t gn = stage_lo + my_lo + found;
-                        if (BINS) {
-                            // credited tests: every bin before it, plus itself when it already existed
-                            my_evals += (unsigned long long)gn + ((was_opened >> found) & 1u);
-                            was_opened |= 1u << found;
-                        }
-                        touched |= 1u << found;
-                        if (lane == 0) {
-                            p.placed[(int64_t)tile * kTile + slot_cur] = (int32_t)gn;
-                            atomicAnd(&alive_w[slot_cur >> 5], ~(1u << (slot_cur & 31)));
-                        }
-                        ++n_placed;
-                    } else if (!last) {
-                        if (lane == 0) out_q[out] = e;  // one word, self-validating: no fence needed
-                        ++out;
-                    }
-                    ++head;
-                    if (e_n == 0) {  // the producer had not written it yet: wait for it now
-                        for (unsigned spins = 0; (e_n = in_q[head]) == 0;)
-                            if (++spins > (1u << 27)) { atomicExch(p.status, 2); e_n = kQueueEnd; break; }
-                        if (e_n != kQueueEnd) {
-                            load_row<D>(r_n, rows + (size_t)(e_n - 1) * D);
-                            c_n = cand[e_n - 1];
-                            slot_n = slot_of[e_n - 1];
-                        }
-                    }
-                    e = e_n;
-                    c = c_n;
-                    slot_cur = slot_n;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) r[d] = r_n[d];
+                        for (int d = 0; d < D; ++d) r[d] = r_next[d];
+                    }
+                    __syncwarp();
+                    n_placed += __popc(took);
+                    if (tracing) t_loop += clock64() - t_l0;
+                    if (placed_here >= 0) {  // bookkeeping off the critical path, one lane per placed entry
+                        p.placed[(int64_t)tile * kTile + s_l] = (int32_t)(stage_lo + my_lo + placed_here);
+                        atomicAnd(&alive_w[s_l >> 5], ~(1u << (s_l & 31)));
+                    }
+                    head += (unsigned)n_ent;
+                    done = endmask != 0;
+                    if (tracing) { const long long now = clock64(); tb += now - t_mark; t_mark = now; }
                 }
                 if (!last && lane == 0) out_q[out] = kQueueEnd;
                 if (lane == 0 && n_placed) atomicAdd(&misc[4], (unsigned)n_placed);
-                if (touched) {
+                if (tracing && lane == 0 && tile < 4096)
+                    p.trace[(size_t)(4096 + tile) * 8 + warp] = ((unsigned long long)(tb >> 2) & 0xFFFFF) |
+                        (((unsigned long long)(t_loop >> 2) & 0xFFFFF) << 20) | ((unsigned long long)(head & 0xFFF) << 40) |
+                        ((unsigned long long)(n_batches & 0xFF) << 52);
+                if (n_placed) {
+                    if (BINS) my_evals += (unsigned long long)ev_local + (unsigned long long)n_placed * (unsigned long long)(stage_lo + my_lo);
                     if (n < Tn) {
 #pragma unroll
                         for (int d = 0; d < D; ++d) state_s[(size_t)d * Tn + n] = S[d];
                     }
                     if (lane == 0) {
-                        if (BINS) opened[warp] = was_opened;
-                        else dirty[warp] = touched;
+                        if (BINS) opened[warp] = touched_or_open;
+                        else dirty[warp] = touched_or_open;
                     }
                 }
             }
@@ -434,38 +522,32 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         ACSFIT_PROF(3)
         if (p.prof && tid == 0) { prof_acc[6] += nh; prof_acc[7] += 1; }
-        // ---- publish the surviving pods of the tile --------------------------------------------
-        if (warp == 0) {
-            const unsigned n_placed_tile = misc[4];
-            forwarded += (long long)total - (long long)n_placed_tile;
-            if (lane < kTile / 32) {
-                const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
-                if (wj * 32 < p.M && n_placed_tile) __stcg(p.alive + wj, alive_w[lane]);
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                st_release(p.progress + stage, tile + 1);
-                misc[3] = n_placed_tile ? 1u : 0u;
-                misc[4] = 0;
-            }
-        }
-        __syncthreads();
-        ACSFIT_PROF(4)
+        const unsigned n_placed_tile = nh ? misc[4] : 0u;
 
         // ---- nodes: refresh the scan thresholds of the nodes that took a pod (all threads) ----
-        if (!BINS && misc[3]) {
+        if (!BINS && n_placed_tile) {
             for (int i = tid; i < Tn * D; i += kThreads) {
                 const int d = i / Tn, n = i - d * Tn;
                 if ((dirty[n >> 5] >> (n & 31)) & 1u)
                     thr_s[i] = node_threshold(cap_s[i], state_s[i]);
             }
-            __syncthreads();
-            if (tid < 8) dirty[tid] = 0;
-            if (tid == 0) misc[3] = 0;
-            __syncthreads();
         }
         ACSFIT_PROF(5)
+
+        // ---- publish the surviving pods of the tile (warp 0; the others go on to the next tile) ----
+        if (warp == 0) {
+            forwarded += (long long)total - (long long)n_placed_tile;
+            if (lane < kTile / 32 && n_placed_tile) {
+                const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
+                if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_release(p.progress + stage, tile + 1);
+            }
+        }
+        ACSFIT_PROF(4)
         if (p.prof && p.trace && tid == 0 && stage == p.trace_stage) {
             for (int i = 0; i < 6; ++i) {
                 p.trace[(size_t)tile * 8 + i] = prof_acc[i] - trace_prev[i];
@@ -477,6 +559,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     }
 #undef ACSFIT_PROF
     // ---- stage end: write the mutated node state back -------------------------------------
+    __syncthreads();
     if (!BINS) {
         for (int i = tid; i < Tn * D; i += kThreads) {
             const int n = i / D, d = i - n * D;

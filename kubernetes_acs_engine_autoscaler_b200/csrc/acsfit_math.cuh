@@ -81,6 +81,34 @@ ACSFIT_HD double node_threshold(double cap, double used)
 {
     if (!fits_node(cap, used, 0.0)) return -1.0;
     if (fits_node(cap, used, bits_to_double(kInfBits))) return bits_to_double(kInfBits);
+    // Fast path.  fl(used + r) <= cap  <=>  used + r lies below the midpoint between cap and its
+    // upper neighbour (or on it, when cap's last bit is even), so thr sits within a few ulps of
+    //     t1 = (cap - used) + (nextup(cap) - cap) / 2.
+    // We do NOT trust that arithmetic: the six neighbours of t1 are probed with the literal predicate
+    // and the answer is taken only when the boundary fits(x_k) && !fits(x_{k+1}) is actually seen;
+    // anything else (specials, huge exponent gaps) falls through to the exact search below.
+    {
+        const double gap = bits_to_double(double_to_bits(cap) + 1ull) - cap;  // cap >= 0 here (fits(0) held)
+        const double t1 = (cap - used) + 0.5 * gap;
+        if (t1 > 0.0 && t1 < 1.7e308 && cap > 0.0) {
+            const uint64_t b = double_to_bits(t1);
+            if (b >= 4ull && b + 3ull < kInfBits) {
+                bool f[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int k = 0; k < 7; ++k) f[k] = fits_node(cap, used, bits_to_double(b - 3ull + (uint64_t)k));
+                if (f[0] && !f[6]) {
+                    int last = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int k = 1; k < 6; ++k) last = f[k] ? k : last;  // monotone: the last true
+                    return bits_to_double(b - 3ull + (uint64_t)last);
+                }
+            }
+        }
+    }
     // gallop from the obvious guess cap - used, then bisect.  invariant: fits(lo), !fits(hi).
     double guess = cap - used;
     uint64_t g = (guess >= 0.0) ? double_to_bits(guess) : 0ull;  // NaN -> 0

@@ -75,6 +75,11 @@ def main():
             sel = list(act[:6]) + list(act[np.argsort(-tr[act, 3])[:10]])
             for t_ in sel:
                 print("     tile %4d: %s | %d %d" % (t_, " ".join("%7d" % v for v in tr[t_, :6]), tr[t_, 6], tr[t_, 7]))
+                if t_ < 4096 and tr[t_, 6] > 0:
+                    w = tr[4096 + t_]
+                    print("        warps (busy/wait cycles, entries, batches): " + "  ".join(
+                        "w%d %d/%d e%d b%d" % (i, (int(v) & 0xFFFFF) * 4, ((int(v) >> 20) & 0xFFFFF) * 4, (int(v) >> 40) & 0xFFF, (int(v) >> 52) & 0xFF)
+                        for i, v in enumerate(w) if v))
         top = np.argsort(-(tot - pr[:, 0]))[:4]
         for s_ in top:
             print("   stage %4d: " % s_ + ", ".join("%s %.0fk" % (n, pr[s_, i] / 1e3) for i, n in enumerate(names))
