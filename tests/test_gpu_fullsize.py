@@ -1,0 +1,108 @@
+"""`-m gpu`: BASELINE.json's full sizes.
+C2 (100k x 10k x 4, 1 pool) is small enough for the plain-C oracle (~2 s): exact comparison.
+C3 (1M x 100k x 8, 8 pools) is checked through size-independent properties of sequential first fit
+(prefix exactness against the oracle, state = ordered sum of the placed requests, idempotence on the
+pending pods, split-run equivalence, decision count recomputed from the placement)."""
+import numpy as np
+import pytest
+import torch
+
+from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn
+from test_gpu_parity import bits, oracle_scale_up, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_full_tick_matches_oracle(engine, oracle_mod):
+    c = syn.make_cluster(100000, 10000, 4, 1, seed=20260923)
+    used0 = syn.initial_used(c)
+    used_o = used0.copy()
+    o = oracle_scale_up(oracle_mod, c, used_o)
+    used_h = used0.copy()
+    h = engine.scale_up_host(c["req"], c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                             c["pool_ignored"], c["over_provision"], c["cap_type"], c["node_type"], used_h)
+    for k in ("feasible", "placed", "acc_pool", "new_size", "units_needed", "bins_opened"):
+        np.testing.assert_array_equal(h[k], o[k], err_msg=k)
+    for k in ("n_to_schedule", "n_pending", "num_unaccounted", "decisions"):
+        assert h[k] == o[k], k
+    np.testing.assert_array_equal(bits(used_h), bits(used_o))
+    assert o["decisions"] > 1.5e9  # the configuration the metric is quoted on
+
+
+def ordered_used(used0, req, placed):
+    """used after counting the placed pods in pod order (numpy, host): the reference's count_pod."""
+    used = used0.copy()
+    idx = np.nonzero(placed >= 0)[0]
+    node = placed[idx]
+    order = np.argsort(node, kind="stable")  # keeps pod order inside every node
+    idx, node = idx[order], node[order]
+    starts = np.nonzero(np.r_[True, node[1:] != node[:-1]])[0]
+    counts = np.diff(np.r_[starts, len(node)])
+    for k in range(int(counts.max()) if len(counts) else 0):
+        sel = counts > k
+        used[node[starts[sel]]] = used[node[starts[sel]]] + req[idx[starts[sel] + k]]
+    return used
+
+
+def test_c3_first_fit_properties(engine, oracle_mod):
+    P, N, D, T = 1000000, 100000, 8, 8
+    c = syn.make_cluster(P, N, D, T, seed=20260924)
+    used0 = syn.initial_used(c)
+    f64, i32 = torch.float64, torch.int32
+    d_req, d_cap, d_type = engine.dev(c["req"], f64), engine.dev(c["cap_type"], f64), engine.dev(c["node_type"], i32)
+    d_used = engine.dev(used0, f64)
+    placed, dec = engine.first_fit_nodes(d_req, None, d_cap, d_type, d_used)
+    placed = to_np(placed)
+    used = to_np(d_used)
+    # (1) the credited decision count is a function of the placement
+    assert int(to_np(dec)[0]) == int(np.where(placed >= 0, placed.astype(np.int64) + 1, N).sum())
+    # (2) the node state is the ordered sum of exactly the placed requests, bit for bit, and never overflows
+    np.testing.assert_array_equal(bits(ordered_used(used0, c["req"], placed)), bits(used))
+    assert (c["cap_type"][c["node_type"]] - used >= 0).all()
+    # (3) sequential first fit is prefix-exact: the first K pods are placed as the oracle places them
+    K = 40000
+    used_o = used0.copy()
+    placed_o, _ = oracle_mod.first_fit_nodes(c["req"][:K], c["cap_type"], c["node_type"], used_o)
+    np.testing.assert_array_equal(placed[:K], placed_o)
+    # (4) idempotence: nodes only fill up, so the pending pods still fit nowhere in the final state
+    pend = np.nonzero(placed < 0)[0].astype(np.int32)
+    d_used2 = d_used.clone()
+    again, _ = engine.first_fit_nodes(d_req, engine.dev(pend, i32), d_cap, d_type, d_used2)
+    assert (to_np(again) == -1).all()
+    np.testing.assert_array_equal(bits(to_np(d_used2)), bits(used))
+    # (5) running the list in two pieces on the carried state equals one run
+    d_used3 = engine.dev(used0, f64)
+    cut = 456789
+    a, _ = engine.first_fit_nodes(d_req, engine.dev(np.arange(cut, dtype=np.int32), i32), d_cap, d_type, d_used3)
+    b, _ = engine.first_fit_nodes(d_req, engine.dev(np.arange(cut, P, dtype=np.int32), i32), d_cap, d_type, d_used3)
+    np.testing.assert_array_equal(np.concatenate([to_np(a), to_np(b)]), placed)
+    np.testing.assert_array_equal(bits(to_np(d_used3)), bits(used))
+
+
+def test_c3_fulfill_properties(engine, oracle_mod):
+    P, D, T = 600000, 8, 8
+    c = syn.make_cluster(P, 64, D, T, seed=20260925)
+    g = engine.fulfill_pending(engine.dev(c["req"], torch.float64), P, c["unit_ordered"], c["pool_actual"],
+                               c["pool_max"], c["pool_ignored"], 1)
+    acc, bin_of = to_np(g["acc_pool"]), to_np(g["bin_of"])
+    unit = c["unit_ordered"]
+    assert g["num_unaccounted"] == int((acc < 0).sum())
+    for t in range(T):
+        sel = acc == t
+        if not sel.any():
+            assert g["bins_opened"][t] == 0 or g["units_needed"][t] >= 0
+            continue
+        b = bin_of[sel]
+        # bins are a dense prefix, every pod is eligible for its pool, and no bin is over-committed
+        assert b.min() == 0 and len(np.unique(b)) == b.max() + 1 == g["bins_opened"][t]
+        assert (unit[t] - c["req"][sel] >= 0).all()
+        load = np.zeros((b.max() + 1, D))
+        np.add.at(load, b, c["req"][sel])
+        assert (load <= unit[t] * (1 + 1e-12)).all()
+        assert g["new_size"][t] == c["pool_actual"][t] + g["units_needed"][t]
+    # first-fit is prefix-exact here too: the oracle on the first K pods opens the same bins for them
+    K = 30000
+    o = oracle_mod.fulfill_pending(c["req"][:K], K, unit, c["pool_actual"], c["pool_max"], c["pool_ignored"], 1)
+    first_pool = int(np.nonzero(g["units_needed"] >= 0)[0][0])
+    sel = o["acc_pool"] == first_pool
+    np.testing.assert_array_equal(bin_of[:K][sel], o["bin_of"][sel])
