@@ -323,6 +323,119 @@ __global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const in
     }
 }
 
+// K1 / K6, warp-cooperative form (D in {2,4,8,16}): a warp owns 32 consecutive nodes; the CSR slice of
+// those nodes is streamed through shared memory in chunks with one row per lane per load (full 16-byte
+// vector loads, consecutive lanes -> consecutive CSR entries), then every lane consumes its own node's
+// entries in order.  The ordered left-to-right float64 sum of the reference is preserved; only the memory
+// access pattern changes (coalesced streaming instead of one scattered row per thread).
+constexpr int kStreamWarps = 8;
+constexpr int kStreamBytesPerWarp = 8192;
+
+template <int D, bool STATES>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ run_idx,
+                   const double *__restrict__ req_run, const uint8_t *__restrict__ flags_run,
+                   const double *__restrict__ cap_type, const int32_t *__restrict__ node_type,
+                   const uint8_t *__restrict__ node_flags, const int64_t *__restrict__ node_age, int64_t N,
+                   int any_pending, const int64_t *__restrict__ idle_threshold, int S,
+                   uint8_t *__restrict__ out_state, double *__restrict__ used_inout)
+{
+    constexpr int kChunk = kStreamBytesPerWarp / (8 * D);
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *rows_s = reinterpret_cast<double *>(stream_smem) + (size_t)warp * kChunk * D;
+    uint8_t *flags_s = stream_smem + (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)warp * kChunk;
+    const int64_t groups = (N + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * kStreamWarps + warp; g < groups; g += (int64_t)gridDim.x * kStreamWarps) {
+        const int64_t n = g * 32 + lane;
+        const bool live = n < N;
+        const int64_t lo = live ? row_ptr[n] : 0, hi = live ? row_ptr[n + 1] : 0;
+        const int64_t k_begin = __shfl_sync(0xFFFFFFFFu, lo, 0);
+        const int64_t n_last = min(g * 32 + 32, N);
+        const int64_t k_end = row_ptr[n_last];
+        double acc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] = (!STATES && live) ? used_inout[(size_t)n * D + d] : 0.0;
+        bool busy = false, undrainable = false;
+        for (int64_t kc = k_begin; kc < k_end; kc += kChunk) {
+            const int len = (int)min((int64_t)kChunk, k_end - kc);
+            for (int e = lane; e < len; e += 32) {
+                const int32_t j = __ldg(run_idx + kc + e);
+                if (STATES) flags_s[e] = __ldg(flags_run + j);
+                const double2 *src = reinterpret_cast<const double2 *>(req_run + (size_t)j * D);
+                double2 *dst = reinterpret_cast<double2 *>(rows_s + (size_t)e * D);
+#pragma unroll
+                for (int d = 0; d < D / 2; ++d) dst[d] = __ldg(src + d);
+            }
+            __syncwarp();
+            const int64_t a = max(lo, kc), b = min(hi, kc + len);
+            for (int64_t k = a; k < b; ++k) {
+                const int e = (int)(k - kc);
+                bool take = true;
+                if (STATES) {
+                    const uint8_t f = flags_s[e];
+                    undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
+                    take = f & ACSFIT_PODF_BUSY;
+                    busy = busy || take;
+                }
+                if (take) {
+                    const double2 *r = reinterpret_cast<const double2 *>(rows_s + (size_t)e * D);
+#pragma unroll
+                    for (int d = 0; d < D / 2; ++d) {
+                        const double2 v = r[d];
+                        acc[2 * d] = __dadd_rn(acc[2 * d], v.x);      // ordered sum, pod-list order
+                        acc[2 * d + 1] = __dadd_rn(acc[2 * d + 1], v.y);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (!live) continue;
+        if (!STATES) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) used_inout[(size_t)n * D + d] = acc[d];
+            continue;
+        }
+        const double *cap = cap_type + (size_t)node_type[n] * D;
+        bool under = true;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            // (UTIL_THRESHOLD * capacity - utilization).possible: multiply THEN subtract, no FMA
+            const double left = __dsub_rn(__dmul_rn(cap[d], 0.3), acc[d]);
+            under = under && (left >= 0.0);
+        }
+        const bool unsched = node_flags[n] & ACSFIT_NODEF_UNSCHEDULABLE;
+        const int64_t age = node_age[n];
+        for (int s = 0; s < S; ++s) {
+            uint8_t st;
+            if (busy && !under) st = unsched ? ACSFIT_ST_BUSY_UNSCHEDULABLE : ACSFIT_ST_BUSY;
+            else if (any_pending && !unsched) st = ACSFIT_ST_POD_PENDING;
+            else if (age <= idle_threshold[s] && !unsched) st = ACSFIT_ST_GRACE_PERIOD;
+            else if (under && (busy || !unsched))
+                st = undrainable ? ACSFIT_ST_UNDER_UTILIZED_UNDRAINABLE : ACSFIT_ST_UNDER_UTILIZED_DRAINABLE;
+            else st = unsched ? ACSFIT_ST_IDLE_UNSCHEDULABLE : ACSFIT_ST_IDLE_SCHEDULABLE;
+            out_state[(size_t)s * N + n] = st;
+        }
+    }
+}
+
+template <int D, bool STATES>
+static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *row_ptr, const int32_t *run_idx,
+                                      const double *req_run, const uint8_t *flags_run, const double *cap_type,
+                                      const int32_t *node_type, const uint8_t *node_flags, const int64_t *node_age,
+                                      int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
+                                      double *used)
+{
+    constexpr int kChunk = kStreamBytesPerWarp / (8 * D);
+    const size_t smem = (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)kStreamWarps * kChunk;
+    auto kern = node_stream_kernel<D, STATES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kStreamWarps * 32, smem, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags,
+                                                node_age, N, any_pending, thr, S, out_state, used);
+    return cudaGetLastError();
+}
+
 // maintain actions ------------------------------------------------------------------------
 constexpr int kMaintBlock = 256;
 constexpr int kMaintRounds = 16;                       // nodes per block = 256 * 16
@@ -886,6 +999,35 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
     return ACSFIT_OK;
 }
 
+// K6 dispatch: the streaming form for padded column counts, the simple per-thread form otherwise
+static acsfit_status run_node_states(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                     const double *req_run, const uint8_t *flags_run, const double *cap_type,
+                                     const int32_t *node_type, const uint8_t *node_flags, const int64_t *node_age,
+                                     int64_t N, int D, int any_pending, const int64_t *thr_dev, int S,
+                                     uint8_t *out_state, cudaStream_t st)
+{
+    if (D == 2 || D == 4 || D == 8 || D == 16) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((N + 31) / 32 + kStreamWarps - 1) / kStreamWarps,
+                                                                      (int64_t)ctx->num_sms * 8));
+        cudaError_t e;
+        switch (D) {
+        case 2: e = launch_node_stream<2, true>(grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr_dev, S, out_state, nullptr); break;
+        case 4: e = launch_node_stream<4, true>(grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr_dev, S, out_state, nullptr); break;
+        case 8: e = launch_node_stream<8, true>(grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr_dev, S, out_state, nullptr); break;
+        default: e = launch_node_stream<16, true>(grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr_dev, S, out_state, nullptr); break;
+        }
+        ++ctx->launches;
+        if (e != cudaSuccess) return fail(ctx, ACSFIT_E_CUDA, "node_states: %s", cudaGetErrorString(e));
+        return ACSFIT_OK;
+    }
+    node_states_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type, node_type,
+                                                             node_flags, node_age, N, D, any_pending, thr_dev, S,
+                                                             out_state);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ABI: device-pointer entry points
 // ---------------------------------------------------------------------------------------------
@@ -915,6 +1057,20 @@ extern "C" acsfit_status acsfit_occupancy(acsfit_ctx *ctx, const int64_t *row_pt
     if (N < 0 || (N > 0 && (!row_ptr || !used_inout)))
         return fail(ctx, ACSFIT_E_INVALID, "occupancy: bad arguments");
     if (N == 0) return ACSFIT_OK;
+    if (D == 2 || D == 4 || D == 8 || D == 16) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((N + 31) / 32 + kStreamWarps - 1) / kStreamWarps,
+                                                                      (int64_t)ctx->num_sms * 8));
+        cudaError_t e;
+        switch (D) {
+        case 2: e = launch_node_stream<2, false>(grid, st, row_ptr, run_idx, req_run, nullptr, nullptr, nullptr, nullptr, nullptr, N, 0, nullptr, 0, nullptr, used_inout); break;
+        case 4: e = launch_node_stream<4, false>(grid, st, row_ptr, run_idx, req_run, nullptr, nullptr, nullptr, nullptr, nullptr, N, 0, nullptr, 0, nullptr, used_inout); break;
+        case 8: e = launch_node_stream<8, false>(grid, st, row_ptr, run_idx, req_run, nullptr, nullptr, nullptr, nullptr, nullptr, N, 0, nullptr, 0, nullptr, used_inout); break;
+        default: e = launch_node_stream<16, false>(grid, st, row_ptr, run_idx, req_run, nullptr, nullptr, nullptr, nullptr, nullptr, N, 0, nullptr, 0, nullptr, used_inout); break;
+        }
+        ++ctx->launches;
+        if (e != cudaSuccess) return fail(ctx, ACSFIT_E_CUDA, "occupancy: %s", cudaGetErrorString(e));
+        return ACSFIT_OK;
+    }
     occupancy_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(row_ptr, run_idx, req_run, N, D, used_inout);
     ++ctx->launches;
     CUDA_TRY(cudaGetLastError());
@@ -989,11 +1145,8 @@ extern "C" acsfit_status acsfit_node_states(acsfit_ctx *ctx, const int64_t *row_
     ctx->arena_off = 0;
     TAKE(thr_dev, int64_t, S);
     CUDA_TRY(cudaMemcpyAsync(thr_dev, idle_threshold, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
-    node_states_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type,
-                                                             node_type, node_flags, node_age, N, D, any_pending,
-                                                             thr_dev, S, out_state);
-    ++ctx->launches;
-    CUDA_TRY(cudaGetLastError());
+    TRY(run_node_states(ctx, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, D,
+                        any_pending, thr_dev, S, out_state, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // idle_threshold is a host buffer
     return ACSFIT_OK;
 }
@@ -1313,10 +1466,8 @@ extern "C" acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *ro
     H2D(d_pool, node_pool, sizeof(int32_t) * (size_t)N);
     H2D(d_pflags, flags_run, (size_t)R);
     H2D(d_nflags, node_flags, (size_t)N);
-    node_states_kernel<<<grid_for(ctx, N, 128), 128, 0, st>>>(d_ptr, d_idx, d_req, d_pflags, d_cap, d_type, d_nflags,
-                                                             d_age, N, D, any_pending, d_thr, 1, d_state);
-    ++ctx->launches;
-    CUDA_TRY(cudaGetLastError());
+    TRY(run_node_states(ctx, d_ptr, d_idx, d_req, d_pflags, d_cap, d_type, d_nflags, d_age, N, D, any_pending, d_thr, 1,
+                        d_state, st));
     TRY(arena_reserve(ctx, maintain_scratch(N, T), st));
     ctx->arena_off = 0;
     TRY(maintain_actions_impl(ctx, d_state, d_pool, N, budget0, pool_scalable, T, dry_run, d_action, st));

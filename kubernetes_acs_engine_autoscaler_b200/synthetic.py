@@ -122,6 +122,40 @@ def make_cluster(P, N, D=4, T=1, seed=0, free_frac=0.15, run_per_node=14, gpu_pr
     }
 
 
+def make_idle_cluster(N, D=4, T=1, seed=0, mean_pods=10.0):
+    """BASELINE config 5: N nodes with a running-pod occupancy list of ~Poisson(mean_pods) small pods each
+    (clipped to the 110-pod limit), 5 % DaemonSet pods, 10 % bare (undrainable) pods, ages log-uniform
+    1 s .. 3 d (wrapped like timedelta.seconds), 2 % cordoned nodes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cap_type = capacity_rows(T, D)
+    node_type = (np.arange(N, dtype=np.int64) % T).astype(np.int32)
+    counts = np.minimum(rng.poisson(mean_pods, size=N), 110).astype(np.int64)
+    row_ptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    R = int(row_ptr[-1])
+    req_run = np.zeros((R, D), dtype=np.float64)
+    scale = np.repeat(np.maximum(1.0, np.floor(cap_type[node_type, CPU] / 2.0)), counts)
+    req_run[:, CPU] = np.array([20, 50, 100, 150], dtype=np.float64)[rng.integers(0, 4, size=R)] * scale * 1e-3
+    req_run[:, MEM] = np.array([32, 64, 128, 256], dtype=np.float64)[rng.integers(0, 4, size=R)] * float(2 ** 20) * scale
+    req_run[:, PODS] = 1.0
+    if D == 8:
+        extra = rng.integers(1, 3, size=(R, 4)).astype(np.float64)
+        extra[rng.random((R, 4)) < 0.8] = 0.0
+        req_run[:, 4:8] = extra
+    flags_run = np.full(R, 1, dtype=np.uint8)
+    r = rng.random(R)
+    flags_run[r < 0.05] = 0
+    flags_run[(r >= 0.05) & (r < 0.15)] |= 2
+    return {
+        "N": N, "D": D, "T": T, "P": 0, "seed": seed, "cap_type": cap_type, "node_type": node_type,
+        "node_pool": node_type.copy(), "row_ptr": row_ptr, "run_idx": np.arange(R, dtype=np.int32),
+        "req_run": req_run, "flags_run": flags_run,
+        "node_flags": (rng.random(N) < 0.02).astype(np.uint8),
+        "node_age": np.exp(rng.uniform(0.0, np.log(3 * 86400.0), size=N)).astype(np.int64) % 86400,
+        "pool_actual": np.bincount(node_type, minlength=T).astype(np.int32),
+    }
+
+
 def initial_used(c):
     """used[N, D] after the occupancy loop (cluster.py:165-168), computed with ordered numpy sums
     (host helper for building inputs; the device path is acsfit_occupancy)."""

@@ -106,3 +106,41 @@ def test_c3_fulfill_properties(engine, oracle_mod):
     first_pool = int(np.nonzero(g["units_needed"] >= 0)[0][0])
     sel = o["acc_pool"] == first_pool
     np.testing.assert_array_equal(bin_of[:K][sel], o["bin_of"][sel])
+
+
+def test_c5_idle_scan_matches_oracle(engine, oracle_mod):
+    """BASELINE config 5 shape (scaled to what the oracle does in seconds): 300k nodes, ~3M running pods,
+    8 idle thresholds, then the maintain decisions in both modes; plus the occupancy sums."""
+    c = syn.make_idle_cluster(300000, 8, 8, seed=31)
+    thr = np.array([60, 300, 900, 1800, 3600, 7200, 21600, 86400], dtype=np.int64)
+    st_o = oracle_mod.node_states(c["row_ptr"], c["run_idx"], c["req_run"], c["flags_run"], c["cap_type"],
+                                  c["node_type"], c["node_flags"], c["node_age"], False, thr)
+    i64, i32, f64, u8 = torch.int64, torch.int32, torch.float64, torch.uint8
+    d_ptr, d_idx, d_req = engine.dev(c["row_ptr"], i64), engine.dev(c["run_idx"], i32), engine.dev(c["req_run"], f64)
+    st = engine.node_states(d_ptr, d_idx, d_req, engine.dev(c["flags_run"], u8), engine.dev(c["cap_type"], f64),
+                            engine.dev(c["node_type"], i32), engine.dev(c["node_flags"], u8),
+                            engine.dev(c["node_age"], i64), False, thr)
+    np.testing.assert_array_equal(to_np(st), st_o)
+    assert len(np.unique(st_o)) >= 5
+    budget = np.array([3, 0, 10 ** 6, -1, 5, 17, 0, 250], dtype=np.int64)
+    scal = np.array([1, 1, 1, 1, 0, 1, 1, 1], dtype=np.uint8)
+    for dry_run in (True, False):
+        s_o, a_o = oracle_mod.maintain_actions(st_o[3], c["node_pool"], budget, scal, dry_run)
+        s_g, a_g = engine.maintain_actions(engine.dev(st_o[3].copy(), u8), engine.dev(c["node_pool"], i32), budget,
+                                           scal, dry_run)
+        np.testing.assert_array_equal(to_np(s_g), s_o)
+        np.testing.assert_array_equal(to_np(a_g), a_o)
+    used_o = np.zeros((c["N"], 8))
+    oracle_mod.occupancy(c["row_ptr"], c["run_idx"], c["req_run"], used_o)
+    d_used = engine.dev(np.zeros((c["N"], 8)), f64)
+    engine.occupancy(d_ptr, d_idx, d_req, d_used)
+    np.testing.assert_array_equal(bits(to_np(d_used)), bits(used_o))
+    # a shuffled pod list (run_idx is a gather, as in the real host layer) gives the same states
+    perm = np.random.default_rng(1).permutation(c["req_run"].shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    st2 = engine.node_states(d_ptr, engine.dev(inv[c["run_idx"]].astype(np.int32), i32),
+                             engine.dev(c["req_run"][perm], f64), engine.dev(c["flags_run"][perm], u8),
+                             engine.dev(c["cap_type"], f64), engine.dev(c["node_type"], i32),
+                             engine.dev(c["node_flags"], u8), engine.dev(c["node_age"], i64), False, thr)
+    np.testing.assert_array_equal(to_np(st2), st_o)
