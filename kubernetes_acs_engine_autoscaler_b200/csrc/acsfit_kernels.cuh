@@ -110,7 +110,7 @@ template <int D, bool BINS>
 struct PipelineSmem {
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)8 * 33 * D /*batch rows*/)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)8 * 36 * D /*batch rows*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + 8 /*opened*/ +
                                      8 /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      7 * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
@@ -144,8 +144,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
     double *state_s = rows + (size_t)kTile * D;                 // [D][Tn]      used (nodes) / remaining (bins)
     double *thr_s = BINS ? state_s : state_s + (size_t)D * Tn;  // [D][Tn]      scan thresholds
     double *cap_s = BINS ? state_s : thr_s + (size_t)D * Tn;    // [D][Tn]      capacity (nodes only)
-    double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [8 warps][33][D] rows of a resolver batch (+1 padding row)
-    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)8 * 33 * D);  // [kTile]
+    double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [8 warps][36][D] rows of a resolver batch (+4 padding rows)
+    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)8 * 36 * D);  // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
     unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
     unsigned *opened = alive_w + kTile / 32;                    // [8] bins: bin already holds a pod (bit per node)
@@ -438,8 +438,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     // reads entry k at a fixed stride and fetches entry k+1 while entry k is being tested.
                     // An entry this warp need not test (its candidate lies in a later warp) is staged with
                     // +inf in dimension 0: the same compare then fails on every lane, without a branch.
-                    double *brow = brows + (size_t)warp * 33 * D;
-                    if (mine) {
+                    double *brow = brows + (size_t)warp * 36 * D;
+                    {   // every lane stages a row: slots past the batch get the same never-fitting +inf row, so the
+                        // loop below always runs its full, unrollable 32 iterations
                         double own[D];
                         load_row<D>(own, rows + (size_t)q_l * D);
                         if (!((testmask >> lane) & 1u)) own[0] = __longlong_as_double(0x7FF0000000000000ll);
@@ -448,14 +449,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             *reinterpret_cast<double2 *>(brow + (size_t)lane * D + d) = make_double2(own[d], own[d + 1]);
                     }
                     __syncwarp();
+                    const unsigned fwdmask = last ? 0u : (n_ent >= 32 ? 0xFFFFFFFFu : ((1u << n_ent) - 1u));
                     double r[D];
                     load_row<D>(r, brow);
                     const long long t_l0 = tracing ? clock64() : 0;
                     unsigned took = 0;  // bit k: entry k of the batch was placed by this warp
-#pragma unroll 2
-                    for (int k = 0; k < n_ent; ++k) {
+                    for (int k0 = 0; k0 < n_ent; k0 += 4)
+#pragma unroll
+                    for (int k = k0; k < k0 + 4; ++k) {  // slots past the batch hold never-fitting rows
                         double r_next[D];
-                        load_row<D>(r_next, brow + (size_t)(k + 1) * D);  // row 32 is padding
+                        load_row<D>(r_next, brow + (size_t)(k + 1) * D);  // rows 32..35 are padding
                         bool ok = true;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
@@ -477,7 +480,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             touched_or_open |= 1u << found;
                             placed_here = lane == k ? found : placed_here;
                             took |= 1u << k;
-                        } else if (!last) {
+                        } else if ((fwdmask >> k) & 1u) {
                             if (lane == k) out_q[out] = e;  // one word, self-validating: no fence needed
                             ++out;
                         }

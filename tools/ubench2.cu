@@ -18,10 +18,11 @@ __global__ void resolver(const double *rows_g, double unit0, double unit1, doubl
                          int *out_placed, int reps)
 {
     __shared__ __align__(16) double rows[NE * D];
-    __shared__ unsigned outq[NE + 1];
-    for (int i = threadIdx.x; i < NE * D; i += 32) rows[i] = rows_g[i];
-    __syncwarp();
-    const int lane = threadIdx.x;
+    __shared__ unsigned outq_all[8][NE + 1];
+    unsigned *outq = outq_all[threadIdx.x >> 5];
+    for (int i = threadIdx.x; i < NE * D; i += blockDim.x) rows[i] = rows_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     long long total = 0;
     int placed_sum = 0;
     for (int rep = 0; rep < reps; ++rep) {
@@ -75,13 +76,13 @@ __global__ void resolver(const double *rows_g, double unit0, double unit1, doubl
 #pragma unroll
                 for (int d = 0; d < D; ++d) r[d] = rn[d];
             }
-            if (placed_here >= 0) out_placed[base + lane] = placed_here;
+            if (placed_here >= 0) out_placed[(threadIdx.x >> 5) * 0 + base + lane] = placed_here;
         }
         total += clock64() - t0;
         placed_sum += n_placed + (int)(evals & 1) + (int)out;
         __syncwarp();
     }
-    if (lane == 0) { *cyc = total; out_placed[NE] = placed_sum; }
+    if (threadIdx.x == 0) { *cyc = total; out_placed[NE] = placed_sum; }
 }
 
 int main()
@@ -99,17 +100,18 @@ int main()
     cudaMalloc(&d, sizeof h); cudaMalloc(&cyc, 8); cudaMalloc(&pl, 4 * (NE + 1));
     cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice);
     const int reps = 200;
-    for (int v = 0; v < 4; ++v) {
+    for (int nw = 1; nw <= 8; nw *= 2)
+    for (int v = 0; v < 1; ++v) {
         long long c = 0;
         for (int it = 0; it < 2; ++it) {
-            if (v == 0) resolver<0><<<1, 32>>>(d, 0.0, 2.0, 7096762368.0, 110.0, cyc, pl, reps);
+            if (v == 0) resolver<0><<<1, 32 * nw>>>(d, 0.0, 2.0, 7096762368.0, 110.0, cyc, pl, reps);
             if (v == 1) resolver<1><<<1, 32>>>(d, 0.0, 2.0, 7096762368.0, 110.0, cyc, pl, reps);
             if (v == 2) resolver<2><<<1, 32>>>(d, 0.0, 2.0, 7096762368.0, 110.0, cyc, pl, reps);
             if (v == 3) resolver<3><<<1, 32>>>(d, 0.0, 2.0, 7096762368.0, 110.0, cyc, pl, reps);
             cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
         }
         int ps; cudaMemcpy(&ps, pl + NE, 4, cudaMemcpyDeviceToHost);
-        printf("variant %d: %.1f cycles / entry  (checksum %d) %s\n", v, (double)c / (reps * NE), ps, cudaGetErrorString(cudaGetLastError()));
+        printf("warps %d variant %d: %.1f cycles / entry  (checksum %d) %s\n", nw, v, (double)c / (reps * NE), ps, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
