@@ -701,10 +701,10 @@ struct StagePlan {
 
 // cut `n_nodes` nodes into stages: the widest stage (<= 1024 nodes) that still gives at
 // least `min_stages` stages, so that every SM has a stage to run.
-static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D)
+static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D, bool bins)
 {
     const int want = ctx->min_stages > 0 ? ctx->min_stages : ctx->num_sms;  // one stage per SM measured best
-    int NS = max_stage_nodes(D) / kNodesPerThread;
+    int NS = max_stage_nodes(D, bins) / kNodesPerThread;
     while (NS > 1 && (n_nodes + (int64_t)NS * kNodesPerThread - 1) / ((int64_t)NS * kNodesPerThread) < want) NS >>= 1;
     StagePlan p;
     p.NS = NS;
@@ -719,9 +719,10 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
 template <int D, bool BINS>
 static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
 {
-    size_t smem = PipelineSmem<D, BINS>::bytes(pp.Tn);
+    constexpr int NT = stage_threads(D, BINS);
+    size_t smem = PipelineSmem<D, BINS, NT>::bytes(pp.Tn);
     if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
-    auto kern = firstfit_pipeline_kernel<D, BINS>;
+    auto kern = firstfit_pipeline_kernel<D, BINS, NT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PipelineParams q = pp;
     q.prof = (ctx->prof_dev && stages <= kProfStages) ? ctx->prof_dev : nullptr;
@@ -731,7 +732,7 @@ static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp
         q.trace = (ctx->trace_stage >= 0 && pp.num_tiles <= kProfTiles) ? ctx->prof_dev + (size_t)kProfStages * 8 : nullptr;
         q.trace_stage = ctx->trace_stage;
     }
-    kern<<<stages, kThreads, smem, st>>>(q);
+    kern<<<stages, NT, smem, st>>>(q);
     ++ctx->launches;
     CUDA_TRY(cudaGetLastError());
     return ACSFIT_OK;
@@ -771,7 +772,7 @@ static void reset_stats(acsfit_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 static size_t first_fit_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N)
 {
-    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0, 16);
+    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0, 16, false);
     return 8192 + sizeof(uint32_t) * (size_t)((P + 31) / 32) + sizeof(int) * ((size_t)plan.stages + 8);
 }
 
@@ -787,7 +788,7 @@ static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const in
         CUDA_TRY(cudaGetLastError());
         return ACSFIT_OK;
     }
-    const StagePlan plan = plan_stages(ctx, N, 0, D);
+    const StagePlan plan = plan_stages(ctx, N, 0, D, false);
     const int64_t alive_words = (P + 31) / 32;
     TAKE(alive, uint32_t, alive_words);
     TAKE(sync_words, int, plan.stages + 8);
@@ -914,7 +915,7 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
             int32_t *list = list_a, *next = list_b;
             int64_t M = E, bin_base = 0;
             while (M > 0) {
-                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D);  // at most one bin per pod
+                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D, true);  // at most one bin per pod
                 CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
                 fill_alive_kernel<<<grid_for(ctx, (M + 31) / 32, 256), 256, 0, st>>>(alive, M);
                 fill_i32_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(placed, M, -1);

@@ -106,20 +106,24 @@ __device__ __forceinline__ void load_row(double (&r)[D], const double *src)
 // dynamic shared memory layout (doubles first for alignment).
 // nodes mode keeps three [D][Tn] arrays: scan thresholds, used (the mutable state) and capacity;
 // bins mode keeps one: the remaining capacity IS the threshold (finite values, Lemma B).
-template <int D, bool BINS>
+template <int D, bool BINS, int NT>
 struct PipelineSmem {
+    static constexpr int NW = NT / 32;  // warps per stage CTA == resolver warps
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)8 * 36 * D /*batch rows*/)
-               + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + 8 /*opened*/ +
-                                     8 /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
-                                     7 * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/)
+               + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
+                                     NW /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
+                                     (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
                + sizeof(unsigned short) * kTile /*slot_of*/;
     }
 };
 
-// one node per lane of the 8 resolver warps
-__host__ __device__ constexpr int max_stage_nodes(int D) { return D <= 8 ? 256 : 128; }
+// threads per stage CTA (the kernel is generic in it; 16-warp stages of 512 bins were measured and do not
+// beat 8 warps: the placement chain, not stage straddling, bounds bin packing)
+__host__ __device__ constexpr int stage_threads(int /*D*/, bool /*bins*/) { return 256; }
+// one node per lane of the resolver warps; 128 for D = 16 keeps shared memory small
+__host__ __device__ constexpr int max_stage_nodes(int D, bool bins) { return D <= 8 ? stage_threads(D, bins) : 128; }
 
 // spin on a shared-memory queue word until the producer warp has written it (0 = not yet)
 __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, int *status)
@@ -133,28 +137,29 @@ __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, in
     return e;
 }
 
-template <int D, bool BINS>
-__global__ void __launch_bounds__(kThreads)
+template <int D, bool BINS, int NT>
+__global__ void __launch_bounds__(NT)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
     constexpr int K = kNodesPerThread;
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = p.Tn;
     double *rows = reinterpret_cast<double *>(smem_raw);        // [kTile][D]   compacted pod rows of the tile
     double *state_s = rows + (size_t)kTile * D;                 // [D][Tn]      used (nodes) / remaining (bins)
     double *thr_s = BINS ? state_s : state_s + (size_t)D * Tn;  // [D][Tn]      scan thresholds
     double *cap_s = BINS ? state_s : thr_s + (size_t)D * Tn;    // [D][Tn]      capacity (nodes only)
-    double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [8 warps][36][D] rows of a resolver batch (+4 padding rows)
-    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)8 * 36 * D);  // [kTile]
+    double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [NW warps][36][D] rows of a resolver batch (+4 padding rows)
+    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)NW * 36 * D);  // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
     unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
-    unsigned *opened = alive_w + kTile / 32;                    // [8] bins: bin already holds a pod (bit per node)
-    unsigned *dirty = opened + 8;                               // [8] nodes: threshold is stale (bit per node)
-    unsigned *wcount = dirty + 8;                               // [8]
+    unsigned *opened = alive_w + kTile / 32;                    // [NW] bins: bin already holds a pod (bit per node)
+    unsigned *dirty = opened + NW;                              // [NW] nodes: threshold is stale (bit per node)
+    unsigned *wcount = dirty + NW;                              // [8]
     unsigned *misc = wcount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
     unsigned *hitlist = misc + 8;                               // [kTile+1] ordered hit entries (q+1), then kQueueEnd
-    unsigned *queue = hitlist + (kTile + 1);                    // [7][kTile+1] forward queue of warp w -> w+1
-    unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + 7 * (kTile + 1) + 1);  // [kTile]
+    unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
+    unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -174,7 +179,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     const int n_warps = (n_valid + 31) >> 5;                     // resolver warps that own a real node
 
     // ---- stage start: state + thresholds of this stage's nodes into shared memory ----------
-    for (int i = tid; i < Tn * D; i += kThreads) {
+    for (int i = tid; i < Tn * D; i += NT) {
         const int n = i / D, d = i - n * D;
         if (BINS) {
             // untouched bin: remaining == unit (scaler.py:145-146); padding bins never fit
@@ -192,17 +197,17 @@ firstfit_pipeline_kernel(const PipelineParams p)
             thr_s[(size_t)d * Tn + n] = t;
         }
     }
-    if (tid < 8) {
+    if (tid < NW) {
         opened[tid] = 0;
         dirty[tid] = 0;
     }
-    for (int i = tid; i < 8 * (kTile + 1) + 1; i += kThreads) hitlist[i] = 0;  // hit list + the 7 queues
+    for (int i = tid; i < NW * (kTile + 1) + 1; i += NT) hitlist[i] = 0;  // hit list + the NW-1 queues
     __syncthreads();
 
     const int NS = p.NS;
     const int slot = tid & (NS - 1);
     const int group = tid / NS;
-    const int PG = kThreads / NS;
+    const int PG = NT / NS;
     unsigned long long my_evals = 0;
     long long forwarded = 0;  // (warp 0) pods this stage passed on to the next one
     unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (thread 0) wait/load/scan/resolve/publish/refresh/hits/tiles
@@ -221,7 +226,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     double pre[D];
     auto prefetch_row = [&](int tile) {
         const int64_t j = (int64_t)tile * kTile + tid;
-        if (tile < p.num_tiles && j < p.M) {
+        if (tid < kTile && tile < p.num_tiles && j < p.M) {
             int64_t row = p.pod_idx ? (int64_t)__ldg(p.pod_idx + j) : j;
             if (p.row_map) row = (int64_t)__ldg(p.row_map + row);
             const double *src = p.req + (size_t)row * D;
@@ -267,16 +272,14 @@ firstfit_pipeline_kernel(const PipelineParams p)
 
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
         const int64_t j = (int64_t)tile * kTile + tid;
-        const unsigned word = (j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
+        const unsigned word = (tid < kTile && j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
         const bool is_alive = (word >> lane) & 1u;
-        if (lane == 0) {
+        if (lane == 0 && warp < kTile / 32) {
             wcount[warp] = __popc(word);
             alive_w[warp] = word;
         }
-        if (tid < kTile / 32) {
-            hitmask[tid] = 0;
-            dirty[tid] = 0;
-        }
+        if (tid < kTile / 32) hitmask[tid] = 0;
+        if (tid < NW) dirty[tid] = 0;
         if (tid == 0) misc[4] = 0;
         __syncthreads();
         unsigned base = 0, total = 0;
@@ -310,7 +313,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (BINS) {
             int n_open = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) n_open += __popc(opened[w]);
+            for (int w = 0; w < NW; ++w) n_open += __popc(opened[w]);
             all_hit = n_open < n_valid;
         }
         if (all_hit) {
@@ -370,7 +373,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
             nh = ht;
             if (nh > 0) {
                 // queue entries: 0 = not written yet, q + 1 = compacted pod position q, kQueueEnd = end
-                const unsigned hw = hitmask[warp];
+                const unsigned hw = warp < kTile / 32 ? hitmask[warp] : 0u;  // CTAs may have more warps than tile words
                 if ((hw >> lane) & 1u) hitlist[hb + __popc(hw & ((1u << lane) - 1u))] = (unsigned)tid + 1u;
                 if (tid == 0) hitlist[ht] = kQueueEnd;
             }
@@ -500,7 +503,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 }
                 if (!last && lane == 0) out_q[out] = kQueueEnd;
                 if (lane == 0 && n_placed) atomicAdd(&misc[4], (unsigned)n_placed);
-                if (tracing && lane == 0 && tile < 4096)
+                if (tracing && lane == 0 && tile < 4096 && warp < 8)
                     p.trace[(size_t)(4096 + tile) * 8 + warp] = ((unsigned long long)(tb >> 2) & 0xFFFFF) |
                         (((unsigned long long)(t_loop >> 2) & 0xFFFFF) << 20) | ((unsigned long long)(head & 0xFFF) << 40) |
                         ((unsigned long long)(n_batches & 0xFF) << 52);
@@ -529,7 +532,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
 
         // ---- nodes: refresh the scan thresholds of the nodes that took a pod (all threads) ----
         if (!BINS && n_placed_tile) {
-            for (int i = tid; i < Tn * D; i += kThreads) {
+            for (int i = tid; i < Tn * D; i += NT) {
                 const int d = i / Tn, n = i - d * Tn;
                 if ((dirty[n >> 5] >> (n & 31)) & 1u)
                     thr_s[i] = node_threshold(cap_s[i], state_s[i]);
@@ -564,7 +567,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     // ---- stage end: write the mutated node state back -------------------------------------
     __syncthreads();
     if (!BINS) {
-        for (int i = tid; i < Tn * D; i += kThreads) {
+        for (int i = tid; i < Tn * D; i += NT) {
             const int n = i / D, d = i - n * D;
             if (n < n_valid) p.used[(size_t)(stage_lo + n) * D + d] = state_s[(size_t)d * Tn + n];
         }
