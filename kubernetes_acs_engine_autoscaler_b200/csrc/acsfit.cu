@@ -704,11 +704,12 @@ struct StagePlan {
 static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D, bool bins)
 {
     const int want = ctx->min_stages > 0 ? ctx->min_stages : ctx->num_sms;  // one stage per SM measured best
-    int NS = max_stage_nodes(D, bins) / kNodesPerThread;
-    while (NS > 1 && (n_nodes + (int64_t)NS * kNodesPerThread - 1) / ((int64_t)NS * kNodesPerThread) < want) NS >>= 1;
+    const int K = nodes_per_thread(D);
+    int NS = max_stage_nodes(D, bins) / K;
+    while (NS > 1 && (n_nodes + (int64_t)NS * K - 1) / ((int64_t)NS * K) < want) NS >>= 1;
     StagePlan p;
     p.NS = NS;
-    p.Tn = NS * kNodesPerThread;
+    p.Tn = NS * K;
     int64_t stages = (n_nodes + p.Tn - 1) / p.Tn;
     if (stages < 1) stages = 1;
     if (max_stages > 0 && stages > max_stages) stages = max_stages;

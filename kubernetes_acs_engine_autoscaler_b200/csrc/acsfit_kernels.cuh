@@ -34,8 +34,8 @@ namespace acsfit {
 
 constexpr int kTile = 256;         // pods per tile == threads per CTA
 constexpr int kThreads = 256;
-constexpr int kNodesPerThread = 4; // K: node rows a thread keeps in registers in the scan
-constexpr int kMaxStageNodes = kThreads * kNodesPerThread;  // 1024 (upper bound; see max_stage_nodes)
+// K: node rows a scanning thread keeps in registers -- K * D = 16 doubles whatever the dimension count
+__host__ __device__ constexpr int nodes_per_thread(int D) { return D <= 4 ? 4 : D <= 8 ? 2 : 1; }
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
 constexpr int kMinBatch = 8;  // entries a consumer warp waits for before it starts a batch
@@ -141,7 +141,7 @@ template <int D, bool BINS, int NT>
 __global__ void __launch_bounds__(NT)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
-    constexpr int K = kNodesPerThread;
+    constexpr int K = nodes_per_thread(D);
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = p.Tn;
@@ -328,27 +328,43 @@ firstfit_pipeline_kernel(const PipelineParams p)
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int d = 0; d < D; ++d) t[k][d] = thr_s[(size_t)d * Tn + slot + k * NS];
-            for (unsigned qb = 0; qb < total; qb += PG) {  // warp-uniform trip count (votes inside)
-                const unsigned q = qb + group;
-                const bool live = q < total;
-                double r[D];
-                load_row<D>(r, rows + (size_t)(live ? q : total - 1) * D);
-                unsigned best = kNoCand;
+            // two pods per iteration: their compares are independent, which keeps the fp64 pipe fed with
+            // only eight warps per stage; trip count is warp-uniform (votes inside)
+            for (unsigned qb = 0; qb < total; qb += 2 * PG) {
+                const unsigned qa = qb + group, qc = qb + PG + group;
+                const bool live_a = qa < total, live_c = qc < total;
+                double ra[D], rc[D];
+                load_row<D>(ra, rows + (size_t)(live_a ? qa : total - 1) * D);
+                load_row<D>(rc, rows + (size_t)(live_c ? qc : total - 1) * D);
+                unsigned best_a = kNoCand, best_c = kNoCand;
 #pragma unroll
                 for (int k = K - 1; k >= 0; --k) {
-                    bool ok = live;
+                    bool ok_a = live_a, ok_c = live_c;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) ok = ok & (r[d] <= t[k][d]);
-                    if (ok) best = (unsigned)(slot + k * NS);
+                    for (int d = 0; d < D; ++d) {
+                        ok_a = ok_a & (ra[d] <= t[k][d]);
+                        ok_c = ok_c & (rc[d] <= t[k][d]);
+                    }
+                    if (ok_a) best_a = (unsigned)(slot + k * NS);
+                    if (ok_c) best_c = (unsigned)(slot + k * NS);
                 }
-                // hits are rare: one vote, and only then a segmented min over the lanes that share q
+                // hits are rare: one vote, and only then a segmented min over the lanes that share a pod
                 // (NS consecutive lanes, or the whole warp when NS >= 32) before a single shared atomic
-                if (__any_sync(0xFFFFFFFFu, best != kNoCand)) {
+                if (__any_sync(0xFFFFFFFFu, (best_a & best_c) != kNoCand)) {
                     const int seg = NS < 32 ? NS : 32;
-                    for (int o = seg >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-                    if ((lane & (seg - 1)) == 0 && best != kNoCand) {
-                        atomicMin(&cand[q], best);
-                        atomicOr(&hitmask[q >> 5], 1u << (q & 31));
+                    for (int o = seg >> 1; o > 0; o >>= 1) {
+                        best_a = min(best_a, __shfl_xor_sync(0xFFFFFFFFu, best_a, o));
+                        best_c = min(best_c, __shfl_xor_sync(0xFFFFFFFFu, best_c, o));
+                    }
+                    if ((lane & (seg - 1)) == 0) {
+                        if (best_a != kNoCand) {
+                            atomicMin(&cand[qa], best_a);
+                            atomicOr(&hitmask[qa >> 5], 1u << (qa & 31));
+                        }
+                        if (best_c != kNoCand) {
+                            atomicMin(&cand[qc], best_c);
+                            atomicOr(&hitmask[qc >> 5], 1u << (qc & 31));
+                        }
                     }
                 }
             }
