@@ -1,10 +1,21 @@
-"""Environment-driven settings (same variables as reference autoscaler/config.py:4-6)."""
+"""Process-wide settings taken from the environment -- the same two variables the reference reads
+(autoscaler/config.py:4-6), so an existing deployment's manifest keeps working.
+
+CAPACITY_DATA         path of the instance-type table: a JSON object {type: {resource: amount}} whose key
+                      ORDER is the pools' cost order (reference capacity.py:34-36).
+CAPACITY_CPU_RESERVE  CPU (cores, float) held back on every instance type for system pods.
+"""
 import os
 
 
+def _from_env(name, default, convert=str):
+    raw = os.environ.get(name)
+    return default if raw is None else convert(raw)
+
+
 class Config(object):
-    # path of the instance-type table (JSON object: type -> {resource: amount}); its key ORDER is
-    # the pools' cost order (reference capacity.py:34-36)
-    CAPACITY_DATA = os.environ.get('CAPACITY_DATA', 'data/capacity.json')
-    # CPU held back on every instance type for system pods
-    CAPACITY_CPU_RESERVE = float(os.environ.get('CAPACITY_CPU_RESERVE', 0.0))
+    pass
+
+
+Config.CAPACITY_DATA = _from_env('CAPACITY_DATA', 'data/capacity.json')
+Config.CAPACITY_CPU_RESERVE = _from_env('CAPACITY_CPU_RESERVE', 0.0, float)
