@@ -37,6 +37,9 @@ struct acsfit_ctx {
     uint64_t launches = 0;
     // pipeline statistics of the last first-fit / bin-pack call
     bool timing = false;
+    bool overlap = true;          // chain the first pool's bin pipeline behind the node pipeline (two streams)
+    cudaStream_t side = nullptr;  // second stream for that
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long *prof_dev = nullptr;  // developer probe buffer [kProfStages][8] + trace [kProfTiles][8]
     int trace_stage = -1;
     std::vector<unsigned long long> prof_host;
@@ -250,6 +253,45 @@ __global__ void scatter_bins_kernel(const int32_t *list, const int32_t *placed, 
     }
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, o));
     if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(max_bin, m);
+}
+
+// bins already assigned by a chained first pass: copy into bin_of and track the highest bin
+__global__ void record_bins_kernel(const int32_t *cur_bin, int64_t P, int32_t *bin_of, int *max_bin)
+{
+    int m = -1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = cur_bin[i];
+        if (b >= 0) {
+            bin_of[i] = b;
+            m = max(m, b);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(max_bin, m);
+}
+struct NegPredI32 {
+    const int32_t *v;
+    __device__ bool operator()(int64_t i) const { return v[i] < 0; }
+};
+// out[i] = src[idx[i]]
+__global__ void gather_i32_kernel(const int32_t *src, const int32_t *idx, int64_t n, int32_t *out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = src[idx[i]];
+}
+// count pods that are feasible for some pool but not eligible for one given pool
+__global__ void count_ineligible_kernel(const uint8_t *feasible, const double *req, int64_t P, int D,
+                                        const double *unit, unsigned long long *out)
+{
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
+        if (feasible[i]) {
+            bool all = true;
+            for (int d = 0; d < D; ++d) all = all && fits_bin(unit[d], req[(size_t)i * D + d]);
+            c += all ? 0 : 1;
+        }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // scaler.py:172-175: pods of the first `take` bins become accounted
@@ -568,6 +610,13 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
         return ACSFIT_E_CUDA;
     }
     if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
+    if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
+    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return ACSFIT_E_CUDA;
+    }
     *out_ctx = ctx;
     return ACSFIT_OK;
 }
@@ -580,6 +629,9 @@ extern "C" acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx)
     if (ctx->hbuf) cudaFree(ctx->hbuf);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
     return ACSFIT_OK;
 }
@@ -855,12 +907,21 @@ static size_t fulfill_scratch(int64_t Pp, int T, int D)
 }
 
 // req row of pending pod p is req[(row_map ? row_map[p] : p) * D]
+// a first bin-packing pass that already ran (chained behind the node pipeline): for pool `pool` every pending
+// pod was eligible, cur_bin[p] holds its bin (or -1) over bins [0, bins_covered), `evals` its credited tests
+struct FirstPassDone {
+    int pool;
+    const int32_t *cur_bin;
+    int64_t bins_covered;
+    uint64_t evals;
+};
+
 static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int32_t *row_map, int64_t Pp,
                                   int64_t num_listed, int D, const double *unit_host, const int32_t *pool_actual,
                                   const int32_t *pool_max, const uint8_t *pool_ignored, int T, int64_t over_provision,
                                   int64_t *out_new_size, int64_t *out_units_needed, int64_t *out_bins_opened,
                                   int32_t *out_acc_pool, int32_t *out_bin_of, int64_t *out_unaccounted,
-                                  uint64_t *out_evals, cudaStream_t st)
+                                  uint64_t *out_evals, cudaStream_t st, const FirstPassDone *pre = nullptr)
 {
     for (int i = 0; i < T * D; ++i)
         if (!std::isfinite(unit_host[i])) return fail(ctx, ACSFIT_E_DOMAIN, "fulfill_pending: non-finite unit capacity");
@@ -901,7 +962,12 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
         if (pool_ignored[t] || !num_unaccounted) continue;  // scaler.py:128-129
 
         int64_t nb = 0, E = 0;
-        if (Pp > 0) {
+        const bool first_done = pre && pre->pool == t && Pp > 0;
+        if (first_done) {
+            // the gate held for every pending pod and the first pass over bins [0, bins_covered) is done
+            E = Pp;
+            evals += (uint64_t)unique_unaccounted + pre->evals;
+        } else if (Pp > 0) {
             // pool gate (scaler.py:134) over the not-yet-accounted pods -> ordered list of eligible pods
             eligible_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(req, row_map, Pp, D, unit_dev + (size_t)t * D,
                                                                    out_acc_pool, elig);
@@ -910,11 +976,19 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
             TRY(compact(ctx, FlagPred{elig}, Pp, nullptr, list_a, block_counts, total_dev, &E, st));
         }
         if (E > 0) {
-            fill_i32_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(cur_bin, Pp, -1);
-            ++ctx->launches;
             CUDA_TRY(cudaMemsetAsync(max_bin_dev, 0xFF, sizeof(int), st));  // -1
             int32_t *list = list_a, *next = list_b;
             int64_t M = E, bin_base = 0;
+            if (first_done) {
+                CUDA_TRY(cudaMemcpyAsync(cur_bin, pre->cur_bin, sizeof(int32_t) * Pp, cudaMemcpyDeviceToDevice, st));
+                record_bins_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(cur_bin, Pp, out_bin_of, max_bin_dev);
+                ++ctx->launches;
+                TRY(compact(ctx, NegPredI32{cur_bin}, Pp, nullptr, list_a, block_counts, total_dev, &M, st));
+                bin_base = pre->bins_covered;
+            } else {
+                fill_i32_kernel<<<grid_for(ctx, Pp, 256), 256, 0, st>>>(cur_bin, Pp, -1);
+                ++ctx->launches;
+            }
             while (M > 0) {
                 const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D, true);  // at most one bin per pod
                 CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
@@ -1203,6 +1277,133 @@ extern "C" acsfit_status acsfit_maintain_actions(acsfit_ctx *ctx, uint8_t *io_st
     return maintain_actions_impl(ctx, io_state, node_pool, N, budget0, pool_scalable, T, dry_run, out_action, st);
 }
 
+// resident stage CTAs the device can hold for the nodes pipeline (all of them must be running before a
+// chained bins pipeline may spin on their progress counters)
+template <int D, bool BINS>
+static int stage_capacity_t(const acsfit_ctx *ctx, int Tn)
+{
+    constexpr int NT = stage_threads(D, BINS);
+    const size_t smem = std::max(PipelineSmem<D, BINS, NT>::bytes(Tn), (size_t)ctx->smem_floor_kb * 1024);
+    auto kern = firstfit_pipeline_kernel<D, BINS, NT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess) return 0;
+    return per_sm * ctx->num_sms;
+}
+// stage CTAs of BOTH pipelines that can be resident together (conservatively: the smaller of the two
+// per-kernel occupancies, slots taken as interchangeable)
+static int chained_capacity(const acsfit_ctx *ctx, int D, int Tn_nodes, int Tn_bins)
+{
+    switch (D) {
+    case 2: return std::min(stage_capacity_t<2, false>(ctx, Tn_nodes), stage_capacity_t<2, true>(ctx, Tn_bins));
+    case 4: return std::min(stage_capacity_t<4, false>(ctx, Tn_nodes), stage_capacity_t<4, true>(ctx, Tn_bins));
+    case 8: return std::min(stage_capacity_t<8, false>(ctx, Tn_nodes), stage_capacity_t<8, true>(ctx, Tn_bins));
+    case 16: return std::min(stage_capacity_t<16, false>(ctx, Tn_nodes), stage_capacity_t<16, true>(ctx, Tn_bins));
+    default: return 0;
+    }
+}
+
+// get_pending_pods with the FIRST pool's bin packing chained behind it: the bins pipeline runs on a second
+// stream and its stage 0 consumes every tile as soon as the last node stage has published it, so the two
+// sequential placement chains overlap instead of adding up.  Only valid when every pod of the list is
+// eligible for that pool (the caller checks) and all node stages are resident at once (checked here).
+// bins_f[j] = bin of list entry j over bins [0, *bins_covered), or -1.
+static acsfit_status first_fit_chained(acsfit_ctx *ctx, const double *req, const int32_t *list_f, int64_t F, int D,
+                                       const double *cap_type, const int32_t *node_type, double *used, int64_t N,
+                                       int32_t *placed_f, unsigned long long *decisions_dev,
+                                       const double *unit_row_dev, int32_t *bins_f, int64_t *bins_covered,
+                                       uint64_t *bin_evals, bool *did, cudaStream_t st)
+{
+    *did = false;
+    const StagePlan pn = plan_stages(ctx, N, 0, D, false);
+    StagePlan pb = plan_stages(ctx, F, kMaxStagesPerPass, D, true);
+    // every stage CTA of both pipelines must be resident at the same time: the bins stages spin on the node
+    // stages' counters, and the two grids are dispatched in no particular order
+    const int room = chained_capacity(ctx, D, pn.Tn, pb.Tn) - pn.stages;
+    if (room < 8) return ACSFIT_OK;  // node stages (nearly) fill the device: no chaining
+    pb.stages = std::min(pb.stages, room);
+    const int64_t alive_words = (F + 31) / 32;
+    TAKE(alive, uint32_t, alive_words);
+    TAKE(sync_n, int, pn.stages + 8);
+    TAKE(sync_b, int, pb.stages + 8);
+    TAKE(evals_dev, unsigned long long, 1);
+    CUDA_TRY(cudaMemsetAsync(decisions_dev, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(evals_dev, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(sync_n, 0, sizeof(int) * (pn.stages + 8), st));
+    CUDA_TRY(cudaMemsetAsync(sync_b, 0, sizeof(int) * (pb.stages + 8), st));
+    fill_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(placed_f, F, -1);
+    fill_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(bins_f, F, -1);
+    fill_alive_kernel<<<grid_for(ctx, alive_words, 256), 256, 0, st>>>(alive, F);
+    ctx->launches += 3;
+
+    PipelineParams a;
+    memset(&a, 0, sizeof a);
+    a.req = req;
+    a.pod_idx = list_f;
+    a.M = F;
+    a.alive = alive;
+    a.placed = placed_f;
+    a.cap_type = cap_type;
+    a.node_type = node_type;
+    a.used = used;
+    a.node_lo = 0;
+    a.node_hi = N;
+    a.Tn = pn.Tn;
+    a.NS = pn.NS;
+    a.num_tiles = (int)((F + kTile - 1) / kTile);
+    a.ticket = sync_n;
+    a.status = sync_n + 1;
+    a.drained = sync_n + 2;
+    a.progress = sync_n + 8;
+    a.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+
+    PipelineParams b = a;
+    b.placed = bins_f;
+    b.cap_type = nullptr;
+    b.node_type = nullptr;
+    b.used = nullptr;
+    b.unit = unit_row_dev;
+    b.bin_base = 0;
+    b.node_lo = 0;
+    b.node_hi = (int64_t)pb.stages * pb.Tn;
+    b.Tn = pb.Tn;
+    b.NS = pb.NS;
+    b.ticket = sync_b;
+    b.status = sync_n + 1;  // one abort word for both pipelines
+    b.drained = sync_b + 2;
+    b.progress = sync_b + 8;
+    b.upstream = a.progress + (pn.stages - 1);
+    b.evals = evals_dev;
+
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+    TRY(launch_pipeline<false>(ctx, D, a, pn.stages, st));        // nodes first: its CTAs are dispatched first
+    CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    TRY(launch_pipeline<true>(ctx, D, b, pb.stages, ctx->side));
+    CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+    decisions_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(placed_f, F, N, decisions_dev);
+    ++ctx->launches;
+    unsigned long long ev = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ev, evals_dev, sizeof ev, cudaMemcpyDeviceToHost, st));
+    TRY(check_pipeline_status(ctx, a.status, st));
+    ctx->last_stages += pn.stages + pb.stages;
+    ctx->last_tiles += 2 * a.num_tiles;
+    if (ctx->timing) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms += ms;
+        unsigned long long d = 0;
+        CUDA_TRY(cudaMemcpy(&d, decisions_dev, sizeof d, cudaMemcpyDeviceToHost));
+        ctx->last_decisions += d;
+    }
+    *bins_covered = (int64_t)pb.stages * pb.Tn;
+    *bin_evals = ev;
+    *did = true;
+    return ACSFIT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused scale-up tick: get_pods_to_schedule + get_pending_pods + fulfill_pending
 // (reference cluster.py:169-175, :206-215) on DEVICE buffers
@@ -1228,8 +1429,8 @@ struct NegPred {
 static size_t scale_up_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N, int T, int D)
 {
     const size_t nblocks = (size_t)((P + kCompactChunk - 1) / kCompactChunk) + 1;
-    return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + sizeof(int32_t) * (size_t)P * 5 +
-           sizeof(int) * nblocks + sizeof(double) * (size_t)T * D + 65536;
+    return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + sizeof(int32_t) * (size_t)P * 8 +
+           sizeof(int) * (nblocks + kMaxStagesPerPass + 16) + sizeof(double) * (size_t)T * D * 2 + 65536;
 }
 
 static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P, int D, const double *unit_all_host,
@@ -1266,13 +1467,54 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
         ctx->launches += 3;
         TRY(compact(ctx, FlagPred{out_feasible}, P, nullptr, list_f, block_counts, total_dev, &F, st));
     }
-    // get_pending_pods (cluster.py:184-204)
+    // get_pending_pods (cluster.py:184-204); when every pod to schedule is eligible for the first pool the
+    // scaler will visit, that pool's bin packing is chained behind it on a second stream
     int64_t Pn = 0;
+    FirstPassDone pre;
+    bool chained = false;
     if (F > 0) {
-        TRY(first_fit_impl(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1, st));
+        int t0 = 0;
+        while (t0 < T && pool_ignored[t0]) ++t0;
+        if (ctx->overlap && N > 0 && t0 < T) {
+            TAKE(unit_ord_dev, double, (size_t)T * D);
+            TAKE(bins_f, int32_t, F);
+            TAKE(j_of_p, int32_t, F);
+            TAKE(cur_bin_p, int32_t, F);
+            TAKE(inel_dev, unsigned long long, 1);
+            CUDA_TRY(cudaMemcpyAsync(unit_ord_dev, unit_ordered_host, sizeof(double) * T * D, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(inel_dev, 0, sizeof(unsigned long long), st));
+            count_ineligible_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_feasible, req, P, D,
+                                                                          unit_ord_dev + (size_t)t0 * D, inel_dev);
+            ++ctx->launches;
+            unsigned long long inel = 1;
+            CUDA_TRY(cudaMemcpyAsync(&inel, inel_dev, sizeof inel, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (inel == 0) {
+                int64_t covered = 0;
+                uint64_t bev = 0;
+                TRY(first_fit_chained(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1,
+                                      unit_ord_dev + (size_t)t0 * D, bins_f, &covered, &bev, &chained, st));
+                if (chained) {
+                    // pending pods in list order: their feasible positions, pod numbers and first-pass bins
+                    TRY(compact(ctx, NegPred{placed_f}, F, nullptr, j_of_p, block_counts, total_dev, &Pn, st));
+                    if (Pn > 0) {
+                        gather_i32_kernel<<<grid_for(ctx, Pn, 256), 256, 0, st>>>(list_f, j_of_p, Pn, list_p);
+                        gather_i32_kernel<<<grid_for(ctx, Pn, 256), 256, 0, st>>>(bins_f, j_of_p, Pn, cur_bin_p);
+                        ctx->launches += 2;
+                    }
+                    pre.pool = t0;
+                    pre.cur_bin = cur_bin_p;
+                    pre.bins_covered = covered;
+                    pre.evals = bev;
+                }
+            }
+        }
+        if (!chained) {
+            TRY(first_fit_impl(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1, st));
+            TRY(compact(ctx, NegPred{placed_f}, F, list_f, list_p, block_counts, total_dev, &Pn, st));
+        }
         scatter_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(list_f, placed_f, F, out_placed);
         ++ctx->launches;
-        TRY(compact(ctx, NegPred{placed_f}, F, list_f, list_p, block_counts, total_dev, &Pn, st));
     }
     unsigned long long ev[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(ev, evals_dev, sizeof ev, cudaMemcpyDeviceToHost, st));
@@ -1289,7 +1531,7 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
         uint64_t fe = 0;
         TRY(fulfill_impl(ctx, req, list_p, Pn, Pn, D, unit_ordered_host, pool_actual, pool_max, pool_ignored, T,
                          over_provision, out_new_size, out_units_needed, out_bins_opened, acc_p, bin_p, &unaccounted,
-                         &fe, st));
+                         &fe, st, chained ? &pre : nullptr));
         decisions += fe;
         scatter_i32_kernel<<<grid_for(ctx, Pn, 256), 256, 0, st>>>(list_p, acc_p, Pn, out_acc_pool);
         ++ctx->launches;

@@ -67,6 +67,8 @@ struct PipelineParams {
     int *progress;          // num_stages ints, zeroed: tiles published by the stage
     int *status;            // 1 int, zeroed: != 0 -> abort (watchdog)
     int *drained;           // 1 int, zeroed: set by the first stage that forwards no pod at all
+    const int *upstream;    // optional: progress counter of ANOTHER pipeline's last stage that feeds stage 0
+                            // of this one (bins pipeline chained behind the nodes pipeline), or nullptr
     unsigned long long *evals; // bins mode: credited bin tests (atomicAdd)
     unsigned long long watchdog_ns;
     unsigned long long *prof;  // optional [stages][8] clock64 phase totals (developer probe), or nullptr
@@ -244,11 +246,11 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (p.prof && tid == 0) tp = clock64();
         // ---- wait until the previous stage has published this tile (warp 1 polls, so that warp 0
         //      can still be publishing the previous tile) ---------------------------------------
-        if (stage > 0) {
+        if (stage > 0 || p.upstream) {
             if (tid == 32) {
-                const int *flag = p.progress + (stage - 1);
+                const int *flag = stage > 0 ? p.progress + (stage - 1) : p.upstream;
                 unsigned spins = 0;
-                if (*(volatile int *)p.drained) {
+                if (stage > 0 && *(volatile int *)p.drained) {
                     // an earlier stage finished with nothing left alive: every remaining tile is empty
                     misc[2] = 1;
                 } else
