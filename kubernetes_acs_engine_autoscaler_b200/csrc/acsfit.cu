@@ -1319,7 +1319,7 @@ static acsfit_status first_fit_chained(acsfit_ctx *ctx, const double *req, const
     StagePlan pb = plan_stages(ctx, F, kMaxStagesPerPass, D, true);
     // every stage CTA of both pipelines must be resident at the same time: the bins stages spin on the node
     // stages' counters, and the two grids are dispatched in no particular order
-    const int room = chained_capacity(ctx, D, pn.Tn, pb.Tn) - pn.stages;
+    const int room = chained_capacity(ctx, D, pn.Tn, pb.Tn) - pn.stages - 4;  // a little headroom
     if (room < 8) return ACSFIT_OK;  // node stages (nearly) fill the device: no chaining
     pb.stages = std::min(pb.stages, room);
     const int64_t alive_words = (F + 31) / 32;

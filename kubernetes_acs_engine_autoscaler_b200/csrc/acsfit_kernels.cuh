@@ -320,10 +320,6 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         if (all_hit) {
             if (tid < total) cand[tid] = 0;
-            if (tid < kTile / 32) {
-                const int lo = tid * 32;
-                hitmask[tid] = (int)total >= lo + 32 ? 0xFFFFFFFFu : ((int)total > lo ? (1u << (total - lo)) - 1u : 0u);
-            }
         } else {
             double t[K][D];
 #pragma unroll
@@ -351,25 +347,32 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     if (ok_c) best_c = (unsigned)(slot + k * NS);
                 }
                 // hits are rare: one vote, and only then a segmented min over the lanes that share a pod
-                // (NS consecutive lanes, or the whole warp when NS >= 32) before a single shared atomic
+                // (NS consecutive lanes; when NS > 32 several warps share the pod and an atomic min merges them)
                 if (__any_sync(0xFFFFFFFFu, (best_a & best_c) != kNoCand)) {
                     const int seg = NS < 32 ? NS : 32;
                     for (int o = seg >> 1; o > 0; o >>= 1) {
                         best_a = min(best_a, __shfl_xor_sync(0xFFFFFFFFu, best_a, o));
                         best_c = min(best_c, __shfl_xor_sync(0xFFFFFFFFu, best_c, o));
                     }
+                    // with NS <= 32 exactly one segment handles a given pod: a plain store; wider stages
+                    // spread a pod over NS / 32 warps, whose minima an atomic merges
                     if ((lane & (seg - 1)) == 0) {
-                        if (best_a != kNoCand) {
-                            atomicMin(&cand[qa], best_a);
-                            atomicOr(&hitmask[qa >> 5], 1u << (qa & 31));
-                        }
-                        if (best_c != kNoCand) {
-                            atomicMin(&cand[qc], best_c);
-                            atomicOr(&hitmask[qc >> 5], 1u << (qc & 31));
+                        if (NS <= 32) {
+                            if (best_a != kNoCand) cand[qa] = best_a;
+                            if (best_c != kNoCand) cand[qc] = best_c;
+                        } else {
+                            if (best_a != kNoCand) atomicMin(&cand[qa], best_a);
+                            if (best_c != kNoCand) atomicMin(&cand[qc], best_c);
                         }
                     }
                 }
             }
+        }
+        __syncthreads();
+        {   // hit mask of the tile from the candidates (no shared atomics in the scan)
+            const bool hit = tid < (int)total && cand[tid] != kNoCand;
+            const unsigned hw = __ballot_sync(0xFFFFFFFFu, hit);
+            if (lane == 0 && warp < kTile / 32) hitmask[warp] = hw;
         }
         __syncthreads();
         ACSFIT_PROF(2)

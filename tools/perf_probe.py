@@ -67,6 +67,7 @@ def main():
         names = ["wait", "load", "scan", "resolve", "publish", "refresh"]
         tot = pr[:, :6].sum(axis=1)
         print("   [%s] stages %d; per-stage busy cycles: max %.3g mean %.3g" % (tag, len(pr), tot.max(), tot.mean()))
+        print("   resolver entries over all stages: %d (tiles with hits: %d)" % (pr[:, 6].sum(), (pr[:, 6] > 0).sum()))
         print("   phase sums over stages (Mcycles): " + ", ".join("%s %.1f" % (n, pr[:, i].sum() / 1e6) for i, n in enumerate(names)))
         tr = eng.debug_trace(args.trace_stage).astype(np.int64)
         act = np.nonzero(tr[:, :6].sum(axis=1))[0]
