@@ -38,7 +38,7 @@ constexpr int kThreads = 256;
 __host__ __device__ constexpr int nodes_per_thread(int D) { return D <= 4 ? 4 : D <= 8 ? 2 : 1; }
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
-constexpr int kMinBatch = 8;  // entries a consumer warp waits for before it starts a batch
+constexpr int kMinBatch = 4;  // entries a consumer warp waits for before it starts a batch
 constexpr int kMaxDims = 16;
 
 struct PipelineParams {
@@ -412,6 +412,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     S[d] = n < Tn ? state_s[(size_t)d * Tn + n] : (BINS ? -1.0 : 0.0);
                     C[d] = (!BINS && n < Tn) ? cap_s[(size_t)d * Tn + n] : -1.0;
                 }
+                // per-dimension maximum a pod may request and still fit SOME node of this warp: an upper bound.
+                // bins: the largest remaining amount; nodes: the largest tile-start threshold (exact at tile start,
+                // and thresholds only shrink while the tile is resolved).
+                double Mx[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    double v = BINS ? S[d] : (n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0);
+                    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+                    Mx[d] = v;
+                }
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned ev_local = 0;
@@ -458,31 +468,42 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     // nodes before cand[q] did not fit at tile start, hence not now either
                     const unsigned testmask = __ballot_sync(0xFFFFFFFFu, mine && (int)c_l < my_lo + 32);
                     int placed_here = -1;  // lane i: LOCAL node (of this warp) that took entry i of the batch
-                    // stage the batch's rows contiguously (lane i copies its own row) so that the loop below
-                    // reads entry k at a fixed stride and fetches entry k+1 while entry k is being tested.
-                    // An entry this warp need not test (its candidate lies in a later warp) is staged with
-                    // +inf in dimension 0: the same compare then fails on every lane, without a branch.
+                    // Which entries of the batch can this warp take at all?  Lane i checks its own entry against
+                    // the per-dimension maximum over the warp's 32 nodes (an upper bound that only gets looser
+                    // as nodes fill up, so a "no" is final) - 32 entries in one step.  Only the entries that
+                    // pass are staged, densely, for the sequential loop; the others are forwarded in bulk.
+                    // (In the scan every pair is compared; this bound only spares the resolver, which sees <= 2 %
+                    // of the pairs, from re-testing pods against a warp whose nodes are all too full.)
                     double *brow = brows + (size_t)warp * 36 * D;
-                    {   // every lane stages a row: slots past the batch get the same never-fitting +inf row, so the
-                        // loop below always runs its full, unrollable 32 iterations
-                        double own[D];
-                        load_row<D>(own, rows + (size_t)q_l * D);
-                        if (!((testmask >> lane) & 1u)) own[0] = __longlong_as_double(0x7FF0000000000000ll);
+                    double own[D];
+                    load_row<D>(own, rows + (size_t)q_l * D);
+                    bool poss = (testmask >> lane) & 1u;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) poss = poss & (own[d] <= Mx[d]);
+                    const unsigned possmask = __ballot_sync(0xFFFFFFFFu, poss);
+                    const int n_poss = __popc(possmask);
+                    const int my_rank = __popc(possmask & ((1u << lane) - 1u));
+                    if (poss) {
 #pragma unroll
                         for (int d = 0; d < D; d += 2)
-                            *reinterpret_cast<double2 *>(brow + (size_t)lane * D + d) = make_double2(own[d], own[d + 1]);
+                            *reinterpret_cast<double2 *>(brow + (size_t)my_rank * D + d) = make_double2(own[d], own[d + 1]);
+                    }
+                    if (lane < 4) {
+                        double *pad = brow + (size_t)(n_poss + lane) * D;
+                        pad[0] = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+                        for (int d = 1; d < D; ++d) pad[d] = 0.0;
                     }
                     __syncwarp();
-                    const unsigned fwdmask = last ? 0u : (n_ent >= 32 ? 0xFFFFFFFFu : ((1u << n_ent) - 1u));
                     double r[D];
                     load_row<D>(r, brow);
                     const long long t_l0 = tracing ? clock64() : 0;
-                    unsigned took = 0;  // bit k: entry k of the batch was placed by this warp
-                    for (int k0 = 0; k0 < n_ent; k0 += 4)
+                    unsigned took = 0;  // bit k: dense entry k of the batch was placed by this warp
+                    for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
-                    for (int k = k0; k < k0 + 4; ++k) {  // slots past the batch hold never-fitting rows
+                    for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
                         double r_next[D];
-                        load_row<D>(r_next, brow + (size_t)(k + 1) * D);  // rows 32..35 are padding
+                        load_row<D>(r_next, brow + (size_t)(k + 1) * D);
                         bool ok = true;
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
@@ -502,17 +523,28 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             // the stage/warp base is added once per tile below
                             ev_local += (unsigned)found + ((touched_or_open >> found) & 1u);
                             touched_or_open |= 1u << found;
-                            placed_here = lane == k ? found : placed_here;
+                            placed_here = (poss && my_rank == k) ? found : placed_here;
                             took |= 1u << k;
-                        } else if ((fwdmask >> k) & 1u) {
-                            if (lane == k) out_q[out] = e;  // one word, self-validating: no fence needed
-                            ++out;
                         }
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
                     }
                     __syncwarp();
                     n_placed += __popc(took);
+                    if (BINS && took) {  // tighten the bound: the remaining amounts just shrank
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            double v = S[d];
+                            for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+                            Mx[d] = v;
+                        }
+                    }
+                    if (!last) {
+                        // forward what this warp did not take, in order, with one coalesced store
+                        const unsigned fwd = __ballot_sync(0xFFFFFFFFu, mine && placed_here < 0);
+                        if (mine && placed_here < 0) out_q[out + __popc(fwd & ((1u << lane) - 1u))] = e;
+                        out += __popc(fwd);
+                    }
                     if (tracing) t_loop += clock64() - t_l0;
                     if (placed_here >= 0) {  // bookkeeping off the critical path, one lane per placed entry
                         p.placed[(int64_t)tile * kTile + s_l] = (int32_t)(stage_lo + my_lo + placed_here);
