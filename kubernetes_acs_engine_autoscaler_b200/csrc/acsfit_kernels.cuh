@@ -117,7 +117,7 @@ struct PipelineSmem {
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
                                      NW /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
-               + sizeof(unsigned short) * kTile /*slot_of*/;
+               + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/;
     }
 };
 
@@ -162,6 +162,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     unsigned *hitlist = misc + 8;                               // [kTile+1] ordered hit entries (q+1), then kQueueEnd
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
     unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
+    unsigned char *found_s = reinterpret_cast<unsigned char *>(slot_of + kTile);  // [NW][32] node that took dense entry k
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -475,6 +476,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     // (In the scan every pair is compared; this bound only spares the resolver, which sees <= 2 %
                     // of the pairs, from re-testing pods against a warp whose nodes are all too full.)
                     double *brow = brows + (size_t)warp * 36 * D;
+                    volatile unsigned char *fnd = found_s + warp * 32;
                     double own[D];
                     load_row<D>(own, rows + (size_t)q_l * D);
                     bool poss = (testmask >> lane) & 1u;
@@ -519,18 +521,28 @@ firstfit_pipeline_kernel(const PipelineParams p)
                                     S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
                                                 : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
                             }
-                            // credited tests (bins): every bin before it, plus itself when it already existed;
-                            // the stage/warp base is added once per tile below
-                            ev_local += (unsigned)found + ((touched_or_open >> found) & 1u);
-                            touched_or_open |= 1u << found;
-                            placed_here = (poss && my_rank == k) ? found : placed_here;
+                            // only what the next test needs stays in the loop; the bookkeeping is done once per
+                            // batch from the recorded node numbers
+                            if (lane == 0) fnd[k] = (unsigned char)found;
                             took |= 1u << k;
                         }
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
                     }
                     __syncwarp();
-                    n_placed += __popc(took);
+                    if (took) {
+                        n_placed += __popc(took);
+                        const bool got = poss && ((took >> my_rank) & 1u);
+                        const int found = got ? (int)fnd[my_rank] : -1;
+                        placed_here = found;
+                        const unsigned acc_lanes = __reduce_or_sync(0xFFFFFFFFu, got ? (1u << found) : 0u);
+                        // credited tests (bins): every bin before the chosen one, plus the chosen one unless this
+                        // pod opened it (= the first pod ever placed in that bin); the stage/warp base is added
+                        // once per tile below
+                        ev_local += __reduce_add_sync(0xFFFFFFFFu, got ? (unsigned)found + 1u : 0u) -
+                                    (unsigned)__popc(acc_lanes & ~touched_or_open);
+                        touched_or_open |= acc_lanes;
+                    }
                     if (BINS && took) {  // tighten the bound: the remaining amounts just shrank
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
