@@ -127,6 +127,14 @@ __host__ __device__ constexpr int stage_threads(int /*D*/, bool /*bins*/) { retu
 // one node per lane of the resolver warps; 128 for D = 16 keeps shared memory small
 __host__ __device__ constexpr int max_stage_nodes(int D, bool bins) { return D <= 8 ? stage_threads(D, bins) : 128; }
 
+// An upper bound of the warp-wide maximum of v (v >= 0, or negative for "no node"): the largest high word with
+// the low word saturated -- one integer REDUX per dimension instead of a five-step shuffle ladder on doubles.
+__device__ __forceinline__ double warp_upper_bound(double v)
+{
+    const int hi = __reduce_max_sync(0xFFFFFFFFu, __double2hiint(v));
+    return hi >= 0x7FF00000 ? __longlong_as_double(0x7FF0000000000000ll) : __hiloint2double(hi, (int)0xFFFFFFFFu);
+}
+
 // spin on a shared-memory queue word until the producer warp has written it (0 = not yet)
 __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, int *status)
 {
@@ -418,11 +426,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 // and thresholds only shrink while the tile is resolved).
                 double Mx[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    double v = BINS ? S[d] : (n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0);
-                    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-                    Mx[d] = v;
-                }
+                for (int d = 0; d < D; ++d) Mx[d] = warp_upper_bound(BINS ? S[d] : (n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0));
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned ev_local = 0;
@@ -500,7 +504,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     double r[D];
                     load_row<D>(r, brow);
                     const long long t_l0 = tracing ? clock64() : 0;
-                    unsigned took = 0;  // bit k: dense entry k of the batch was placed by this warp
+                    unsigned took = 0;    // bit k: dense entry k of the batch was placed by this warp
+                    unsigned mymask = 0;  // bit k: ... by THIS lane's node
+                    const unsigned me = 1u << lane;
                     for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
                     for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
@@ -514,21 +520,21 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         }
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                         if (m) {
-                            const int found = __ffs(m) - 1;
-                            if (lane == found) {
+                            if ((m & (0u - m)) == me) {  // the first fitting node of the warp takes the pod
 #pragma unroll
                                 for (int d = 0; d < D; ++d)
                                     S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
                                                 : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
+                                mymask |= 1u << k;
                             }
                             // only what the next test needs stays in the loop; the bookkeeping is done once per
-                            // batch from the recorded node numbers
-                            if (lane == 0) fnd[k] = (unsigned char)found;
+                            // batch from the per-lane masks
                             took |= 1u << k;
                         }
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
                     }
+                    for (unsigned t = mymask; t; t &= t - 1) fnd[__ffs(t) - 1] = (unsigned char)lane;
                     __syncwarp();
                     if (took) {
                         n_placed += __popc(took);
@@ -545,11 +551,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     }
                     if (BINS && took) {  // tighten the bound: the remaining amounts just shrank
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            double v = S[d];
-                            for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-                            Mx[d] = v;
-                        }
+                        for (int d = 0; d < D; ++d) Mx[d] = warp_upper_bound(S[d]);
                     }
                     if (!last) {
                         // forward what this warp did not take, in order, with one coalesced store
