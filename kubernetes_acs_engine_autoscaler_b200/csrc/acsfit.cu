@@ -371,9 +371,9 @@ __global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const in
 // entries in order.  The ordered left-to-right float64 sum of the reference is preserved; only the memory
 // access pattern changes (coalesced streaming instead of one scattered row per thread).
 constexpr int kStreamWarps = 8;
-constexpr int kStreamBytesPerWarp = 8192;
+static int g_stream_bytes = 8192;  // staging bytes per warp (developer knob ACSFIT_STREAM_BYTES: 2048 / 4096 / 8192)
 
-template <int D, bool STATES>
+template <int D, bool STATES, int kStreamBytesPerWarp>
 __global__ void __launch_bounds__(kStreamWarps * 32)
 node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ run_idx,
                    const double *__restrict__ req_run, const uint8_t *__restrict__ flags_run,
@@ -382,11 +382,14 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
                    int any_pending, const int64_t *__restrict__ idle_threshold, int S,
                    uint8_t *__restrict__ out_state, double *__restrict__ used_inout)
 {
-    constexpr int kChunk = kStreamBytesPerWarp / (8 * D);
+    // two staging buffers per warp: chunk c+1 is in flight (cp.async, no register staging) while chunk c is consumed
+    constexpr int kChunk = kStreamBytesPerWarp / 2 / (8 * D);  // CSR entries per chunk
+    constexpr int kIter = kChunk / 32;                         // entries per lane per chunk
+    static_assert(kIter >= 1, "chunk smaller than a warp");
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *rows_s = reinterpret_cast<double *>(stream_smem) + (size_t)warp * kChunk * D;
-    uint8_t *flags_s = stream_smem + (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)warp * kChunk;
+    double *rows_s = reinterpret_cast<double *>(stream_smem) + (size_t)warp * 2 * kChunk * D;
+    uint8_t *flags_s = stream_smem + (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)warp * 2 * kChunk;
     const int64_t groups = (N + 31) / 32;
     for (int64_t g = (int64_t)blockIdx.x * kStreamWarps + warp; g < groups; g += (int64_t)gridDim.x * kStreamWarps) {
         const int64_t n = g * 32 + lane;
@@ -399,29 +402,72 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] = (!STATES && live) ? used_inout[(size_t)n * D + d] : 0.0;
         bool busy = false, undrainable = false;
-        for (int64_t kc = k_begin; kc < k_end; kc += kChunk) {
+        uint8_t fpend[kIter];  // flags of the chunk in flight
+        // all gathers of a chunk are issued before anything waits: indices first, then the row copies, then flags
+        auto issue = [&](int buf, int64_t kc) {
             const int len = (int)min((int64_t)kChunk, k_end - kc);
-            for (int e = lane; e < len; e += 32) {
-                const int32_t j = __ldg(run_idx + kc + e);
-                if (STATES) flags_s[e] = __ldg(flags_run + j);
-                const double2 *src = reinterpret_cast<const double2 *>(req_run + (size_t)j * D);
-                double2 *dst = reinterpret_cast<double2 *>(rows_s + (size_t)e * D);
+            // consecutive lanes copy consecutive 16-byte pieces (D/2 pieces per row): the two halves of a 32-byte
+            // sector are requested by the same instruction
+            constexpr int kPieces = D / 2;
+            int32_t jp[kIter * kPieces];
 #pragma unroll
-                for (int d = 0; d < D / 2; ++d) dst[d] = __ldg(src + d);
+            for (int i = 0; i < kIter * kPieces; ++i) {
+                const int e = (lane + 32 * i) / kPieces;
+                jp[i] = e < len ? __ldg(run_idx + kc + e) : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < kIter * kPieces; ++i) {
+                if (jp[i] >= 0) {
+                    const int piece = lane + 32 * i;
+                    const double *src = req_run + (size_t)jp[i] * D + 2 * (piece % kPieces);
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(rows_s + (size_t)buf * kChunk * D) + 16u * (unsigned)piece;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+            int32_t j[kIter];
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) {
+                const int e = lane + 32 * i;
+                j[i] = (STATES && e < len) ? __ldg(run_idx + kc + e) : -1;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (STATES) {  // flag bytes travel through registers; they are parked in shared memory one chunk later
+#pragma unroll
+                for (int i = 0; i < kIter; ++i) fpend[i] = j[i] >= 0 ? __ldg(flags_run + j[i]) : (uint8_t)0;
+            }
+        };
+        auto park_flags = [&](int buf) {
+            if (STATES) {
+#pragma unroll
+                for (int i = 0; i < kIter; ++i) flags_s[buf * kChunk + lane + 32 * i] = fpend[i];
+            }
+        };
+        int buf = 0;
+        if (k_begin < k_end) issue(0, k_begin);
+        for (int64_t kc = k_begin; kc < k_end; kc += kChunk, buf ^= 1) {
+            const int len = (int)min((int64_t)kChunk, k_end - kc);
+            park_flags(buf);  // requested a whole chunk ago
+            if (kc + kChunk < k_end) {
+                issue(buf ^ 1, kc + kChunk);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncwarp();
+            const double *rows_b = rows_s + (size_t)buf * kChunk * D;
+            const uint8_t *flags_b = flags_s + buf * kChunk;
             const int64_t a = max(lo, kc), b = min(hi, kc + len);
             for (int64_t k = a; k < b; ++k) {
                 const int e = (int)(k - kc);
                 bool take = true;
                 if (STATES) {
-                    const uint8_t f = flags_s[e];
+                    const uint8_t f = flags_b[e];
                     undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
                     take = f & ACSFIT_PODF_BUSY;
                     busy = busy || take;
                 }
                 if (take) {
-                    const double2 *r = reinterpret_cast<const double2 *>(rows_s + (size_t)e * D);
+                    const double2 *r = reinterpret_cast<const double2 *>(rows_b + (size_t)e * D);
 #pragma unroll
                     for (int d = 0; d < D / 2; ++d) {
                         const double2 v = r[d];
@@ -430,7 +476,7 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
                     }
                 }
             }
-            __syncwarp();
+            __syncwarp();  // the buffer is refilled two chunks from now (issued after the next consume starts)
         }
         if (!live) continue;
         if (!STATES) {
@@ -461,6 +507,28 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
     }
 }
 
+template <int D, bool STATES, int kStreamBytesPerWarp>
+static cudaError_t launch_node_stream_b(int grid, cudaStream_t st, const int64_t *row_ptr, const int32_t *run_idx,
+                                      const double *req_run, const uint8_t *flags_run, const double *cap_type,
+                                      const int32_t *node_type, const uint8_t *node_flags, const int64_t *node_age,
+                                      int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
+                                      double *used)
+{
+    constexpr int kChunk = kStreamBytesPerWarp / 2 / (8 * D);
+    const size_t smem = (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)kStreamWarps * 2 * kChunk;
+    auto kern = node_stream_kernel<D, STATES, kStreamBytesPerWarp>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // persistent grid: exactly the CTAs that are resident at once (the caller passes SMs * 8 as an upper bound)
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStreamWarps * 32, smem) == cudaSuccess && per_sm > 0 &&
+        cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+        grid = std::min(grid, per_sm * sms);
+    kern<<<grid, kStreamWarps * 32, smem, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags,
+                                                node_age, N, any_pending, thr, S, out_state, used);
+    return cudaGetLastError();
+}
+
 template <int D, bool STATES>
 static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *row_ptr, const int32_t *run_idx,
                                       const double *req_run, const uint8_t *flags_run, const double *cap_type,
@@ -468,14 +536,11 @@ static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *
                                       int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
                                       double *used)
 {
-    constexpr int kChunk = kStreamBytesPerWarp / (8 * D);
-    const size_t smem = (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)kStreamWarps * kChunk;
-    auto kern = node_stream_kernel<D, STATES>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, kStreamWarps * 32, smem, st>>>(row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags,
-                                                node_age, N, any_pending, thr, S, out_state, used);
-    return cudaGetLastError();
+#define ACSFIT_STREAM_ARGS grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
+    if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_b<D, STATES, 2048>(ACSFIT_STREAM_ARGS); }
+    if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_b<D, STATES, 4096>(ACSFIT_STREAM_ARGS); }
+    return launch_node_stream_b<D, STATES, 8192>(ACSFIT_STREAM_ARGS);
+#undef ACSFIT_STREAM_ARGS
 }
 
 // maintain actions ------------------------------------------------------------------------
@@ -611,6 +676,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     }
     if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
     if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
+    if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -1084,7 +1150,7 @@ static acsfit_status run_node_states(acsfit_ctx *ctx, const int64_t *row_ptr, co
 {
     if (D == 2 || D == 4 || D == 8 || D == 16) {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((N + 31) / 32 + kStreamWarps - 1) / kStreamWarps,
-                                                                      (int64_t)ctx->num_sms * 8));
+                                                                      (int64_t)ctx->num_sms * 16));
         cudaError_t e;
         switch (D) {
         case 2: e = launch_node_stream<2, true>(grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr_dev, S, out_state, nullptr); break;
@@ -1135,7 +1201,7 @@ extern "C" acsfit_status acsfit_occupancy(acsfit_ctx *ctx, const int64_t *row_pt
     if (N == 0) return ACSFIT_OK;
     if (D == 2 || D == 4 || D == 8 || D == 16) {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((N + 31) / 32 + kStreamWarps - 1) / kStreamWarps,
-                                                                      (int64_t)ctx->num_sms * 8));
+                                                                      (int64_t)ctx->num_sms * 16));
         cudaError_t e;
         switch (D) {
         case 2: e = launch_node_stream<2, false>(grid, st, row_ptr, run_idx, req_run, nullptr, nullptr, nullptr, nullptr, nullptr, N, 0, nullptr, 0, nullptr, used_inout); break;
