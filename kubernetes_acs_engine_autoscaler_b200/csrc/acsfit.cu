@@ -382,7 +382,9 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
                    int any_pending, const int64_t *__restrict__ idle_threshold, int S,
                    uint8_t *__restrict__ out_state, double *__restrict__ used_inout)
 {
-    // two staging buffers per warp: chunk c+1 is in flight (cp.async, no register staging) while chunk c is consumed
+    // A warp owns a CONTIGUOUS range of node groups (32 nodes each), hence one contiguous CSR range, which it
+    // streams through two staging buffers without ever draining the pipe: chunk c+1 is in flight (cp.async, no
+    // register staging) while chunk c is consumed, across group boundaries.
     constexpr int kChunk = kStreamBytesPerWarp / 2 / (8 * D);  // CSR entries per chunk
     constexpr int kIter = kChunk / 32;                         // entries per lane per chunk
     static_assert(kIter >= 1, "chunk smaller than a warp");
@@ -391,98 +393,80 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
     double *rows_s = reinterpret_cast<double *>(stream_smem) + (size_t)warp * 2 * kChunk * D;
     uint8_t *flags_s = stream_smem + (size_t)kStreamWarps * kStreamBytesPerWarp + (size_t)warp * 2 * kChunk;
     const int64_t groups = (N + 31) / 32;
-    for (int64_t g = (int64_t)blockIdx.x * kStreamWarps + warp; g < groups; g += (int64_t)gridDim.x * kStreamWarps) {
-        const int64_t n = g * 32 + lane;
-        const bool live = n < N;
-        const int64_t lo = live ? row_ptr[n] : 0, hi = live ? row_ptr[n + 1] : 0;
-        const int64_t k_begin = __shfl_sync(0xFFFFFFFFu, lo, 0);
-        const int64_t n_last = min(g * 32 + 32, N);
-        const int64_t k_end = row_ptr[n_last];
-        double acc[D];
+    const int64_t n_warps = (int64_t)gridDim.x * kStreamWarps;
+    const int64_t per = (groups + n_warps - 1) / n_warps;
+    const int64_t g0 = ((int64_t)blockIdx.x * kStreamWarps + warp) * per;
+    const int64_t g1 = min(groups, g0 + per);
+    if (g0 >= g1) return;
+    const int64_t K0 = row_ptr[g0 * 32], K1 = row_ptr[min(g1 * 32, N)];
+
+    uint8_t fpend[kIter];  // flags of the chunk in flight
+    // the CSR indices of a chunk are fetched one chunk before its rows are requested, so that no gather ever
+    // waits for the index it depends on: round c issues rows(c+1) with indices loaded in round c-1
+    constexpr int kPieces = D / 2;
+    int32_t jp[kIter * kPieces];  // row of the 16-byte piece this lane copies (consecutive lanes, consecutive pieces)
+    int32_t je[kIter];            // row of the entry whose flag byte this lane fetches
+    auto load_idx = [&](int64_t kc) {
+        const int len = (int)min((int64_t)kChunk, K1 - kc);
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = (!STATES && live) ? used_inout[(size_t)n * D + d] : 0.0;
-        bool busy = false, undrainable = false;
-        uint8_t fpend[kIter];  // flags of the chunk in flight
-        // all gathers of a chunk are issued before anything waits: indices first, then the row copies, then flags
-        auto issue = [&](int buf, int64_t kc) {
-            const int len = (int)min((int64_t)kChunk, k_end - kc);
-            // consecutive lanes copy consecutive 16-byte pieces (D/2 pieces per row): the two halves of a 32-byte
-            // sector are requested by the same instruction
-            constexpr int kPieces = D / 2;
-            int32_t jp[kIter * kPieces];
-#pragma unroll
-            for (int i = 0; i < kIter * kPieces; ++i) {
-                const int e = (lane + 32 * i) / kPieces;
-                jp[i] = e < len ? __ldg(run_idx + kc + e) : -1;
-            }
-#pragma unroll
-            for (int i = 0; i < kIter * kPieces; ++i) {
-                if (jp[i] >= 0) {
-                    const int piece = lane + 32 * i;
-                    const double *src = req_run + (size_t)jp[i] * D + 2 * (piece % kPieces);
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(rows_s + (size_t)buf * kChunk * D) + 16u * (unsigned)piece;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                }
-            }
-            int32_t j[kIter];
+        for (int i = 0; i < kIter * kPieces; ++i) {
+            const int e = (lane + 32 * i) / kPieces;
+            jp[i] = e < len ? __ldg(run_idx + kc + e) : -1;
+        }
+        if (STATES) {
 #pragma unroll
             for (int i = 0; i < kIter; ++i) {
                 const int e = lane + 32 * i;
-                j[i] = (STATES && e < len) ? __ldg(run_idx + kc + e) : -1;
+                je[i] = e < len ? __ldg(run_idx + kc + e) : -1;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (STATES) {  // flag bytes travel through registers; they are parked in shared memory one chunk later
-#pragma unroll
-                for (int i = 0; i < kIter; ++i) fpend[i] = j[i] >= 0 ? __ldg(flags_run + j[i]) : (uint8_t)0;
-            }
-        };
-        auto park_flags = [&](int buf) {
-            if (STATES) {
-#pragma unroll
-                for (int i = 0; i < kIter; ++i) flags_s[buf * kChunk + lane + 32 * i] = fpend[i];
-            }
-        };
-        int buf = 0;
-        if (k_begin < k_end) issue(0, k_begin);
-        for (int64_t kc = k_begin; kc < k_end; kc += kChunk, buf ^= 1) {
-            const int len = (int)min((int64_t)kChunk, k_end - kc);
-            park_flags(buf);  // requested a whole chunk ago
-            if (kc + kChunk < k_end) {
-                issue(buf ^ 1, kc + kChunk);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            __syncwarp();
-            const double *rows_b = rows_s + (size_t)buf * kChunk * D;
-            const uint8_t *flags_b = flags_s + buf * kChunk;
-            const int64_t a = max(lo, kc), b = min(hi, kc + len);
-            for (int64_t k = a; k < b; ++k) {
-                const int e = (int)(k - kc);
-                bool take = true;
-                if (STATES) {
-                    const uint8_t f = flags_b[e];
-                    undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
-                    take = f & ACSFIT_PODF_BUSY;
-                    busy = busy || take;
-                }
-                if (take) {
-                    const double2 *r = reinterpret_cast<const double2 *>(rows_b + (size_t)e * D);
-#pragma unroll
-                    for (int d = 0; d < D / 2; ++d) {
-                        const double2 v = r[d];
-                        acc[2 * d] = __dadd_rn(acc[2 * d], v.x);      // ordered sum, pod-list order
-                        acc[2 * d + 1] = __dadd_rn(acc[2 * d + 1], v.y);
-                    }
-                }
-            }
-            __syncwarp();  // the buffer is refilled two chunks from now (issued after the next consume starts)
         }
-        if (!live) continue;
+    };
+    auto issue = [&](int buf) {  // rows (cp.async, no register staging) and flag bytes of the chunk jp/je describe
+#pragma unroll
+        for (int i = 0; i < kIter * kPieces; ++i) {
+            if (jp[i] >= 0) {
+                const int piece = lane + 32 * i;
+                const double *src = req_run + (size_t)jp[i] * D + 2 * (piece % kPieces);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(rows_s + (size_t)buf * kChunk * D) + 16u * (unsigned)piece;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (STATES) {  // flag bytes travel through registers; they are parked in shared memory one chunk later
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) fpend[i] = je[i] >= 0 ? __ldg(flags_run + je[i]) : (uint8_t)0;
+        }
+    };
+    auto park_flags = [&](int buf) {
+        if (STATES) {
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) flags_s[buf * kChunk + lane + 32 * i] = fpend[i];
+        }
+    };
+
+    // per-group state of this lane's node; the next group's row pointers (and used row) are fetched a group ahead
+    int64_t g = g0;
+    int64_t lo, hi, lo_n = 0, hi_n = 0;
+    double acc[D], acc_n[D];
+    bool busy = false, undrainable = false;
+    auto fetch_group = [&](int64_t gg, int64_t &l, int64_t &h, double (&a0)[D]) {
+        const int64_t nn = gg * 32 + lane;
+        l = row_ptr[min(nn, N)];
+        h = row_ptr[min(nn + 1, N)];  // lanes past N get an empty range
+#pragma unroll
+        for (int d = 0; d < D; ++d) a0[d] = (!STATES && nn < N) ? used_inout[(size_t)nn * D + d] : 0.0;
+    };
+    fetch_group(g0, lo, hi, acc);
+    if (g0 + 1 < g1) fetch_group(g0 + 1, lo_n, hi_n, acc_n);
+    int64_t group_end = __shfl_sync(0xFFFFFFFFu, hi, 31);
+
+    auto finalize = [&]() {
+        const int64_t n = g * 32 + lane;
+        if (n >= N) return;
         if (!STATES) {
 #pragma unroll
             for (int d = 0; d < D; ++d) used_inout[(size_t)n * D + d] = acc[d];
-            continue;
+            return;
         }
         const double *cap = cap_type + (size_t)node_type[n] * D;
         bool under = true;
@@ -504,6 +488,68 @@ node_stream_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
             else st = unsched ? ACSFIT_ST_IDLE_UNSCHEDULABLE : ACSFIT_ST_IDLE_SCHEDULABLE;
             out_state[(size_t)s * N + n] = st;
         }
+    };
+
+    int buf = 0;
+    if (K0 < K1) {
+        load_idx(K0);
+        issue(0);
+        if (K0 + kChunk < K1) load_idx(K0 + kChunk);
+    }
+    for (int64_t kc = K0;; kc += kChunk, buf ^= 1) {
+        const bool has_chunk = kc < K1;
+        const int64_t chunk_end = has_chunk ? min(kc + kChunk, K1) : K1;
+        if (has_chunk) {
+            park_flags(buf);  // requested a whole chunk ago
+            if (kc + kChunk < K1) {
+                issue(buf ^ 1);                                          // chunk c+1: its indices are in registers
+                if (kc + 2 * kChunk < K1) load_idx(kc + 2 * kChunk);    // chunk c+2: indices only
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+        }
+        const double *rows_b = rows_s + (size_t)buf * kChunk * D;
+        const uint8_t *flags_b = flags_s + buf * kChunk;
+        // every group with entries in this chunk; a group is closed as soon as its last entry has been seen
+        while (g < g1) {
+            if (has_chunk) {
+                const int64_t a = max(lo, kc), b = min(hi, chunk_end);
+                for (int64_t k = a; k < b; ++k) {
+                    const int e = (int)(k - kc);
+                    bool take = true;
+                    if (STATES) {
+                        const uint8_t f = flags_b[e];
+                        undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
+                        take = f & ACSFIT_PODF_BUSY;
+                        busy = busy || take;
+                    }
+                    if (take) {
+                        const double2 *r = reinterpret_cast<const double2 *>(rows_b + (size_t)e * D);
+#pragma unroll
+                        for (int d = 0; d < D / 2; ++d) {
+                            const double2 v = r[d];
+                            acc[2 * d] = __dadd_rn(acc[2 * d], v.x);      // ordered sum, pod-list order
+                            acc[2 * d + 1] = __dadd_rn(acc[2 * d + 1], v.y);
+                        }
+                    }
+                }
+            }
+            if (group_end > chunk_end) break;  // the group continues in the next chunk
+            finalize();
+            ++g;
+            lo = lo_n;
+            hi = hi_n;
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc[d] = acc_n[d];
+            busy = false;
+            undrainable = false;
+            group_end = __shfl_sync(0xFFFFFFFFu, hi, 31);
+            if (g + 1 < g1) fetch_group(g + 1, lo_n, hi_n, acc_n);
+        }
+        if (g >= g1) break;
+        __syncwarp();  // everyone is done with this buffer before it is refilled (two chunks from now)
     }
 }
 
