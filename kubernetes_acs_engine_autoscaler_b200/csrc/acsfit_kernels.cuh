@@ -335,43 +335,52 @@ firstfit_pipeline_kernel(const PipelineParams p)
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int d = 0; d < D; ++d) t[k][d] = thr_s[(size_t)d * Tn + slot + k * NS];
-            // two pods per iteration: their compares are independent, which keeps the fp64 pipe fed with
-            // only eight warps per stage; trip count is warp-uniform (votes inside)
-            for (unsigned qb = 0; qb < total; qb += 2 * PG) {
-                const unsigned qa = qb + group, qc = qb + PG + group;
-                const bool live_a = qa < total, live_c = qc < total;
-                double ra[D], rc[D];
-                load_row<D>(ra, rows + (size_t)(live_a ? qa : total - 1) * D);
-                load_row<D>(rc, rows + (size_t)(live_c ? qc : total - 1) * D);
-                unsigned best_a = kNoCand, best_c = kNoCand;
+            // several pods per iteration: their compares are independent, which keeps the fp64 pipe fed with
+            // only eight warps per stage, and the vote / loop overhead is paid once per group of pods;
+            // trip count is warp-uniform (votes inside)
+            constexpr int PPI = (D == 8) ? 4 : 2;  // pods per thread and iteration
+            for (unsigned qb = 0; qb < total; qb += PPI * PG) {
+                unsigned q[PPI];
+                bool live[PPI];
+                double r[PPI][D];
+                unsigned best[PPI];
+#pragma unroll
+                for (int i = 0; i < PPI; ++i) {
+                    q[i] = qb + (unsigned)(i * PG + group);
+                    live[i] = q[i] < total;
+                    load_row<D>(r[i], rows + (size_t)(live[i] ? q[i] : total - 1) * D);
+                    best[i] = kNoCand;
+                }
 #pragma unroll
                 for (int k = K - 1; k >= 0; --k) {
-                    bool ok_a = live_a, ok_c = live_c;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        ok_a = ok_a & (ra[d] <= t[k][d]);
-                        ok_c = ok_c & (rc[d] <= t[k][d]);
+                    for (int i = 0; i < PPI; ++i) {
+                        bool ok = live[i];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) ok = ok & (r[i][d] <= t[k][d]);
+                        if (ok) best[i] = (unsigned)(slot + k * NS);
                     }
-                    if (ok_a) best_a = (unsigned)(slot + k * NS);
-                    if (ok_c) best_c = (unsigned)(slot + k * NS);
                 }
                 // hits are rare: one vote, and only then a segmented min over the lanes that share a pod
                 // (NS consecutive lanes; when NS > 32 several warps share the pod and an atomic min merges them)
-                if (__any_sync(0xFFFFFFFFu, (best_a & best_c) != kNoCand)) {
+                unsigned any_best = best[0];
+#pragma unroll
+                for (int i = 1; i < PPI; ++i) any_best &= best[i];
+                if (__any_sync(0xFFFFFFFFu, any_best != kNoCand)) {
                     const int seg = NS < 32 ? NS : 32;
                     for (int o = seg >> 1; o > 0; o >>= 1) {
-                        best_a = min(best_a, __shfl_xor_sync(0xFFFFFFFFu, best_a, o));
-                        best_c = min(best_c, __shfl_xor_sync(0xFFFFFFFFu, best_c, o));
+#pragma unroll
+                        for (int i = 0; i < PPI; ++i) best[i] = min(best[i], __shfl_xor_sync(0xFFFFFFFFu, best[i], o));
                     }
                     // with NS <= 32 exactly one segment handles a given pod: a plain store; wider stages
                     // spread a pod over NS / 32 warps, whose minima an atomic merges
                     if ((lane & (seg - 1)) == 0) {
-                        if (NS <= 32) {
-                            if (best_a != kNoCand) cand[qa] = best_a;
-                            if (best_c != kNoCand) cand[qc] = best_c;
-                        } else {
-                            if (best_a != kNoCand) atomicMin(&cand[qa], best_a);
-                            if (best_c != kNoCand) atomicMin(&cand[qc], best_c);
+#pragma unroll
+                        for (int i = 0; i < PPI; ++i) {
+                            if (best[i] != kNoCand) {
+                                if (NS <= 32) cand[q[i]] = best[i];
+                                else atomicMin(&cand[q[i]], best[i]);
+                            }
                         }
                     }
                 }
