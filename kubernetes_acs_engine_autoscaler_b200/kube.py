@@ -10,8 +10,6 @@ import datetime
 import json
 import logging
 
-from dateutil.parser import parse as dateutil_parse
-
 from . import utils
 
 logger = logging.getLogger('autoscaler.kube')
@@ -77,8 +75,8 @@ class KubePod(object):
         self.labels = meta.get('labels', {})
         self.annotations = meta.get('annotations', {})
         self.owner = self.labels.get('owner', None)
-        self.creation_time = dateutil_parse(meta['creationTimestamp'])
-        self.start_time = dateutil_parse(status['startTime']) if 'startTime' in status else None
+        self.creation_time = utils.parse_time(meta['creationTimestamp'])
+        self.start_time = utils.parse_time(status['startTime']) if 'startTime' in status else None
         # resources = pods:1 + per-key sum over containers, accumulated as 0.0 + v1 + v2 ... in
         # container order (kube.py:41-49): the order fixes the float64 result
         totals = {}
@@ -137,7 +135,7 @@ class KubeNode(object):
         self.capacity = None  # set by Cluster.create_kube_node from the capacity table
         self.used_capacity = KubeResource()
         self.unschedulable = node.obj['spec'].get('unschedulable', False)
-        self.creation_time = dateutil_parse(meta['creationTimestamp'])
+        self.creation_time = utils.parse_time(meta['creationTimestamp'])
         self.instance_index = utils.get_instance_index(node)
 
     def _get_instance_data(self):
