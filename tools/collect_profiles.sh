@@ -12,3 +12,6 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=cs
 python bench.py --steps 10 --warmup 3 > gpurun_out/r01_bench.json 2> gpurun_out/r01_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01_bench_reference.json 2>/dev/null
 tail -c 600 gpurun_out/r01_bench.json
+# idle-node scan (BASELINE config 5): launch list with DRAM bytes of the streaming kernels
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:node_stream -c 10 \
+    --csv --log-file gpurun_out/r01_idle_launches.csv python tools/perf_idle.py > gpurun_out/r01_idle.log 2>&1
