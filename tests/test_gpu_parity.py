@@ -252,3 +252,51 @@ def test_domain_errors(engine):
     with pytest.raises(AcsfitError):  # D not in {2,4,8,16}
         engine.first_fit_nodes(engine.dev(np.ones((10, 3)), torch.float64), None, engine.dev(np.ones((1, 3)), torch.float64),
                                engine.dev(np.zeros(2, np.int32), torch.int32), engine.dev(np.zeros((2, 3)), torch.float64))
+
+
+@pytest.mark.parametrize("N,D,seed", [(1, 2, 0), (31, 4, 1), (33, 4, 2), (1000, 8, 3), (2049, 16, 4), (70000, 4, 5)])
+def test_streaming_kernels_ragged_and_permuted(engine, oracle_mod, N, D, seed):
+    """K1 / K6 with what the warp-streaming form has to get right: a CSR whose index list is a random
+    permutation of the rows (scattered gathers), empty nodes, nodes whose slice spans many staging chunks,
+    node counts that are not a multiple of 32 / of the per-warp range, and every padded dimension count."""
+    rng = np.random.default_rng(100 + seed)
+    counts = rng.poisson(6.0, size=N).astype(np.int64)
+    counts[rng.random(N) < 0.3] = 0                      # runs of empty nodes
+    heavy = rng.integers(0, N, size=max(1, N // 200))
+    counts[heavy] = rng.integers(300, 1500, size=len(heavy))  # slices much longer than a staging chunk
+    row_ptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    R = int(row_ptr[-1])
+    Rtab = R + 17                                        # the row table is larger than the CSR and permuted
+    run_idx = rng.permutation(Rtab)[:R].astype(np.int32)
+    req_run = np.zeros((Rtab, D))
+    req_run[:, 0] = rng.integers(1, 400, size=Rtab).astype(np.float64) * 1e-3
+    req_run[:, 1] = rng.integers(1, 64, size=Rtab).astype(np.float64) * float(2 ** 20)
+    if D > 2:
+        req_run[:, 2:] = rng.integers(0, 3, size=(Rtab, D - 2)).astype(np.float64) * (rng.random((Rtab, D - 2)) < 0.3)
+    flags_run = rng.integers(0, 4, size=Rtab).astype(np.uint8)
+    T = 3
+    cap_type = np.zeros((T, D))
+    cap_type[:, 0] = [2.0, 4.0, 8.0]
+    cap_type[:, 1] = [7e9, 14e9, 28e9]
+    cap_type[:, 2:] = 110.0
+    node_type = rng.integers(0, T, size=N).astype(np.int32)
+    node_flags = (rng.random(N) < 0.1).astype(np.uint8)
+    node_age = rng.integers(0, 86400, size=N).astype(np.int64)
+    thr = np.array([60, 900, 3600, 86400], dtype=np.int64)
+
+    used0 = rng.integers(0, 5, size=(N, D)).astype(np.float64) * 0.125
+    used_o = used0.copy()
+    oracle_mod.occupancy(row_ptr, run_idx, req_run, used_o)
+    d_used = engine.dev(used0, torch.float64)
+    engine.occupancy(engine.dev(row_ptr, torch.int64), engine.dev(run_idx, torch.int32), engine.dev(req_run, torch.float64), d_used)
+    np.testing.assert_array_equal(bits(to_np(d_used)), bits(used_o))
+
+    for any_pending in (False, True):
+        st_o = oracle_mod.node_states(row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age,
+                                      any_pending, thr)
+        st = engine.node_states(engine.dev(row_ptr, torch.int64), engine.dev(run_idx, torch.int32),
+                                engine.dev(req_run, torch.float64), engine.dev(flags_run, torch.uint8),
+                                engine.dev(cap_type, torch.float64), engine.dev(node_type, torch.int32),
+                                engine.dev(node_flags, torch.uint8), engine.dev(node_age, torch.int64), any_pending, thr)
+        np.testing.assert_array_equal(to_np(st), st_o)

@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-template <int D, int K, int PODS>
+template <int D, int K, int PODS, bool SIGN>
 __global__ void scan(const double *rows_g, int n_rows, int reps, long long *cyc, unsigned *sink)
 {
     extern __shared__ __align__(16) double rows[];
@@ -30,8 +30,15 @@ __global__ void scan(const double *rows_g, int n_rows, int reps, long long *cyc,
 #pragma unroll
                 for (int p = 0; p < PODS; ++p) {
                     bool ok = true;
+                    if (SIGN) {
+                        int neg = 0;
 #pragma unroll
-                    for (int d = 0; d < D; ++d) ok = ok & (r[p][d] <= t[k][d]);
+                        for (int d = 0; d < D; ++d) neg |= __double2hiint(__dsub_rn(t[k][d], r[p][d]));
+                        ok = neg >= 0;
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) ok = ok & (r[p][d] <= t[k][d]);
+                    }
                     if (ok) hits += k + p + 1;
                 }
         }
@@ -40,15 +47,15 @@ __global__ void scan(const double *rows_g, int n_rows, int reps, long long *cyc,
     sink[blockIdx.x * blockDim.x + threadIdx.x] = hits;
 }
 
-template <int D, int K, int PODS>
+template <int D, int K, int PODS, bool SIGN>
 void run(const double *d_rows, int n_rows, int warps, long long *cyc, unsigned *sink)
 {
     const int reps = 50;
-    auto kern = scan<D, K, PODS>;
+    auto kern = scan<D, K, PODS, SIGN>;
     for (int it = 0; it < 2; ++it) kern<<<1, warps * 32, n_rows * D * 8>>>(d_rows, n_rows, reps, cyc, sink);
     long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     const double cmp = (double)reps * n_rows * K * D * warps * 32;
-    printf("D=%d K=%d pods/iter=%d warps=%2d: %.1f DSETP lane-ops / cycle / SM (%s)\n", D, K, PODS, warps, cmp / c,
+    printf("%s D=%d K=%d pods/iter=%d warps=%2d: %.1f compare lane-ops / cycle / SM (%s)\n", SIGN ? "DADD+sign" : "DSETP    ", D, K, PODS, warps, cmp / c,
            cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -61,11 +68,11 @@ int main()
     cudaMalloc(&d, sizeof h); cudaMalloc(&cyc, 8 * 8); cudaMalloc(&sink, 4 * 1024);
     cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice);
     for (int w = 8; w <= 16; w += 8) {
-        run<4, 4, 2>(d, n_rows, w, cyc, sink);
-        run<4, 4, 4>(d, n_rows, w, cyc, sink);
-        run<8, 2, 2>(d, n_rows, w, cyc, sink);
-        run<8, 2, 4>(d, n_rows, w, cyc, sink);
-        run<8, 1, 4>(d, n_rows, w, cyc, sink);
+        run<4, 4, 2, false>(d, n_rows, w, cyc, sink); run<4, 4, 2, true>(d, n_rows, w, cyc, sink);
+        run<4, 4, 4, false>(d, n_rows, w, cyc, sink); run<4, 4, 4, true>(d, n_rows, w, cyc, sink);
+        run<8, 2, 2, false>(d, n_rows, w, cyc, sink); run<8, 2, 2, true>(d, n_rows, w, cyc, sink);
+        run<8, 2, 4, false>(d, n_rows, w, cyc, sink); run<8, 2, 4, true>(d, n_rows, w, cyc, sink);
+        run<8, 1, 4, false>(d, n_rows, w, cyc, sink); run<8, 1, 4, true>(d, n_rows, w, cyc, sink);
     }
     return 0;
 }
