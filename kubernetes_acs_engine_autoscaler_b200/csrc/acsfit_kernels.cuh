@@ -113,9 +113,9 @@ struct PipelineSmem {
     static constexpr int NW = NT / 32;  // warps per stage CTA == resolver warps
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/ + (size_t)(NW + 1) * D /*warp bounds + stage bound*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
-                                     NW /*dirty*/ + 8 /*warp counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
+                                     NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
                + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/;
     }
@@ -160,13 +160,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
     double *thr_s = BINS ? state_s : state_s + (size_t)D * Tn;  // [D][Tn]      scan thresholds
     double *cap_s = BINS ? state_s : thr_s + (size_t)D * Tn;    // [D][Tn]      capacity (nodes only)
     double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [NW warps][36][D] rows of a resolver batch (+4 padding rows)
-    unsigned *cand = reinterpret_cast<unsigned *>(brows + (size_t)NW * 36 * D);  // [kTile]
+    double *wmax = brows + (size_t)NW * 36 * D;                 // [NW][D] per-warp upper bound of what still fits a node
+    double *smax = wmax + (size_t)NW * D;                       // [D] the same bound over the whole stage
+    unsigned *cand = reinterpret_cast<unsigned *>(smax + D);    // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
     unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
     unsigned *opened = alive_w + kTile / 32;                    // [NW] bins: bin already holds a pod (bit per node)
     unsigned *dirty = opened + NW;                              // [NW] nodes: threshold is stale (bit per node)
-    unsigned *wcount = dirty + NW;                              // [8]
-    unsigned *misc = wcount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
+    unsigned *wcount = dirty + NW;                              // [8] pods to scan per tile word
+    unsigned *acount = wcount + 8;                              // [8] alive pods per tile word
+    unsigned *misc = acount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
     unsigned *hitlist = misc + 8;                               // [kTile+1] ordered hit entries (q+1), then kQueueEnd
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
     unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
@@ -214,6 +217,30 @@ firstfit_pipeline_kernel(const PipelineParams p)
     }
     for (int i = tid; i < NW * (kTile + 1) + 1; i += NT) hitlist[i] = 0;  // hit list + the NW-1 queues
     __syncthreads();
+
+    // Per-warp, per-dimension upper bound of the request that can still fit SOME node of the warp (nodes: the
+    // scan thresholds, bins: the remaining amounts).  Kept in shared memory, refreshed after every tile that
+    // placed a pod.  Two users: the resolver (skips a whole batch against a full warp) and the tile loader
+    // below, which leaves pods that exceed the bound of EVERY warp in some dimension out of the scan: they can
+    // fit no node of this stage now, hence - state only shrinks - none later in the tile either.  Pruning
+    // earns time, never credit: the credited decisions are derived from the placements, not from the tests run.
+    auto refresh_bounds = [&]() {
+        if (warp < n_warps) {
+            const int n = (warp << 5) + lane;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double b = warp_upper_bound(n < Tn ? (BINS ? state_s[(size_t)d * Tn + n] : thr_s[(size_t)d * Tn + n]) : -1.0);
+                if (lane == 0) wmax[warp * D + d] = b;
+            }
+        }
+        __syncthreads();
+        if (tid < D) {
+            double m = wmax[tid];
+            for (int w = 1; w < n_warps; ++w) m = fmax(m, wmax[w * D + tid]);
+            smax[tid] = m;
+        }
+    };
+    refresh_bounds();  // visible after the first (S1)
 
     const int NS = p.NS;
     const int slot = tid & (NS - 1);
@@ -285,28 +312,37 @@ firstfit_pipeline_kernel(const PipelineParams p)
         const int64_t j = (int64_t)tile * kTile + tid;
         const unsigned word = (tid < kTile && j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
         const bool is_alive = (word >> lane) & 1u;
+        bool pass = is_alive;
+        if (is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
+#pragma unroll
+            for (int d = 0; d < D; ++d) pass = pass & (pre[d] <= smax[d]);
+        }
+        const unsigned pword = __ballot_sync(0xFFFFFFFFu, pass);
         if (lane == 0 && warp < kTile / 32) {
-            wcount[warp] = __popc(word);
+            wcount[warp] = __popc(pword);
+            acount[warp] = __popc(word);
             alive_w[warp] = word;
         }
         if (tid < kTile / 32) hitmask[tid] = 0;
         if (tid < NW) dirty[tid] = 0;
         if (tid == 0) misc[4] = 0;
         __syncthreads();
-        unsigned base = 0, total = 0;
+        unsigned base = 0, total = 0, alive_total = 0;  // total: pods to scan (compacted rows)
 #pragma unroll
         for (int w = 0; w < kTile / 32; ++w) {
             const unsigned c = wcount[w];
             base += (w < warp) ? c : 0u;
             total += c;
+            alive_total += acount[w];
         }
-        if (total == 0) {  // nothing alive: forward the tile untouched
+        if (total == 0) {  // nothing alive, or nothing that could fit here: forward the tile untouched
+            forwarded += (long long)alive_total;
             if (tid == 0) st_release(p.progress + stage, tile + 1);
             prefetch_row(tile + 1);
             continue;  // uniform: every thread sees the same total; (S1) protects the shared words
         }
-        if (is_alive) {
-            const unsigned pos = base + __popc(word & ((1u << lane) - 1u));
+        if (pass) {
+            const unsigned pos = base + __popc(pword & ((1u << lane) - 1u));
             double *dst = rows + (size_t)pos * D;
 #pragma unroll
             for (int d = 0; d < D; d += 2) *reinterpret_cast<double2 *>(dst + d) = make_double2(pre[d], pre[d + 1]);
@@ -435,7 +471,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 // and thresholds only shrink while the tile is resolved).
                 double Mx[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) Mx[d] = warp_upper_bound(BINS ? S[d] : (n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0));
+                for (int d = 0; d < D; ++d) Mx[d] = wmax[warp * D + d];
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned ev_local = 0;
@@ -593,6 +629,12 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         if (BINS) opened[warp] = touched_or_open;
                         else dirty[warp] = touched_or_open;
                     }
+                    if (BINS && lane < D) {  // the bound this warp tightened after its last placing batch
+                        double b = Mx[0];
+#pragma unroll
+                        for (int d = 1; d < D; ++d) b = lane == d ? Mx[d] : b;
+                        wmax[warp * D + lane] = b;
+                    }
                 }
             }
             __syncthreads();
@@ -614,11 +656,25 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     thr_s[i] = node_threshold(cap_s[i], state_s[i]);
             }
         }
+        // node state changed: new bounds for the next tile (visible after its (S1)).  bins: every resolver warp
+        // has already stored the bound it kept tight while placing; nodes: from the refreshed thresholds.
+        if (n_placed_tile) {
+            if (BINS) {
+                if (tid < D) {
+                    double m = wmax[tid];
+                    for (int w = 1; w < n_warps; ++w) m = fmax(m, wmax[w * D + tid]);
+                    smax[tid] = m;
+                }
+            } else {
+                __syncthreads();  // thresholds just rewritten by all threads
+                refresh_bounds();
+            }
+        }
         ACSFIT_PROF(5)
 
         // ---- publish the surviving pods of the tile (warp 0; the others go on to the next tile) ----
         if (warp == 0) {
-            forwarded += (long long)total - (long long)n_placed_tile;
+            forwarded += (long long)alive_total - (long long)n_placed_tile;
             if (lane < kTile / 32 && n_placed_tile) {
                 const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
                 if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
