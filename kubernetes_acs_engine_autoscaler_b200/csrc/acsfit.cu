@@ -26,6 +26,8 @@ struct acsfit_ctx {
     int num_sms = 0;
     int min_stages = 0;       // 0 = number of SMs
     int watchdog_ms = 20000;
+    int resident_nodes[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // cached occupancy answers per D (full-size stages)
+    int prune = -1;           // -1: automatic (node passes that run in waves), 0 / 1: forced (ACSFIT_PRUNE)
     int smem_floor_kb = 0;    // >0: request at least this much dynamic smem per stage CTA (limits CTAs per SM)
     char err[512] = {0};
     // grow-only device arena, bump-allocated per API call
@@ -722,6 +724,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     }
     if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
     if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
+    if (const char *env = getenv("ACSFIT_PRUNE")) ctx->prune = atoi(env);
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -881,14 +884,20 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
     return p;
 }
 
-template <int D, bool BINS>
-static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
+template <int D, bool BINS, bool PRUNE>
+static acsfit_status launch_pipeline_v(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
 {
     constexpr int NT = stage_threads(D, BINS);
-    size_t smem = PipelineSmem<D, BINS, NT>::bytes(pp.Tn);
+    size_t smem = PipelineSmem<D, BINS, NT, PRUNE>::bytes(pp.Tn);
     if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
-    auto kern = firstfit_pipeline_kernel<D, BINS, NT>;
+    auto kern = firstfit_pipeline_kernel<D, BINS, NT, PRUNE>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (resident) {  // only asked: how many stages does the GPU hold at once?
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+        *resident = per_sm * ctx->num_sms;
+        return ACSFIT_OK;
+    }
     PipelineParams q = pp;
     q.prof = (ctx->prof_dev && stages <= kProfStages) ? ctx->prof_dev : nullptr;
     if (q.prof) {
@@ -901,6 +910,26 @@ static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp
     ++ctx->launches;
     CUDA_TRY(cudaGetLastError());
     return ACSFIT_OK;
+}
+
+template <int D, bool BINS>
+static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
+{
+    if (!BINS) {
+        // Stage bounds + scan-list pruning (the PRUNE instantiation) pay when the pass is throughput-bound, i.e.
+        // when there are more stages than the GPU holds at once (waves); a pass that fits is bound by its
+        // placement chain and runs the plain instantiation (measured: c3 nodes pass 143 -> 128 ms with pruning,
+        // c2 tick 10.75 -> 10.93 ms).  ACSFIT_PRUNE=0/1 forces either.
+        int prune = ctx->prune;
+        if (prune < 0) {
+            int &resident = ctx->resident_nodes[D == 2 ? 0 : D == 4 ? 1 : D == 8 ? 2 : 3][pp.Tn == max_stage_nodes(D, false) ? 0 : 1];
+            if (resident <= 0 || pp.Tn != max_stage_nodes(D, false))  // asked once per shape (the query costs ~10 us)
+                TRY((launch_pipeline_v<D, BINS, false>(ctx, pp, stages, st, &resident)));
+            prune = stages > resident;
+        }
+        if (prune) return launch_pipeline_v<D, false, true>(ctx, pp, stages, st, nullptr);
+    }
+    return launch_pipeline_v<D, BINS, false>(ctx, pp, stages, st, nullptr);
 }
 
 template <bool BINS>
@@ -1396,7 +1425,7 @@ static int stage_capacity_t(const acsfit_ctx *ctx, int Tn)
 {
     constexpr int NT = stage_threads(D, BINS);
     const size_t smem = std::max(PipelineSmem<D, BINS, NT>::bytes(Tn), (size_t)ctx->smem_floor_kb * 1024);
-    auto kern = firstfit_pipeline_kernel<D, BINS, NT>;
+    auto kern = firstfit_pipeline_kernel<D, BINS, NT, false>;  // a chained pass fits the GPU, hence runs unpruned
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess) return 0;
@@ -1587,7 +1616,7 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
     if (F > 0) {
         int t0 = 0;
         while (t0 < T && pool_ignored[t0]) ++t0;
-        if (ctx->overlap && N > 0 && t0 < T) {
+        if (ctx->overlap && ctx->prune != 1 && N > 0 && t0 < T) {  // (forced pruning changes the node kernel: no chaining)
             TAKE(unit_ord_dev, double, (size_t)T * D);
             TAKE(bins_f, int32_t, F);
             TAKE(j_of_p, int32_t, F);

@@ -108,12 +108,12 @@ __device__ __forceinline__ void load_row(double (&r)[D], const double *src)
 // dynamic shared memory layout (doubles first for alignment).
 // nodes mode keeps three [D][Tn] arrays: scan thresholds, used (the mutable state) and capacity;
 // bins mode keeps one: the remaining capacity IS the threshold (finite values, Lemma B).
-template <int D, bool BINS, int NT>
+template <int D, bool BINS, int NT, bool PRUNE = false>
 struct PipelineSmem {
     static constexpr int NW = NT / 32;  // warps per stage CTA == resolver warps
     static __host__ __device__ size_t bytes(int Tn)
     {
-        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/ + (size_t)(NW + 1) * D /*warp bounds + stage bound*/)
+        return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/ + (PRUNE ? (size_t)(NW + 1) * D : 0) /*warp bounds + stage bound*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
                                      NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
@@ -147,7 +147,7 @@ __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, in
     return e;
 }
 
-template <int D, bool BINS, int NT>
+template <int D, bool BINS, int NT, bool PRUNE>
 __global__ void __launch_bounds__(NT)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
@@ -162,7 +162,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     double *brows = state_s + (size_t)(BINS ? 1 : 3) * D * Tn;  // [NW warps][36][D] rows of a resolver batch (+4 padding rows)
     double *wmax = brows + (size_t)NW * 36 * D;                 // [NW][D] per-warp upper bound of what still fits a node
     double *smax = wmax + (size_t)NW * D;                       // [D] the same bound over the whole stage
-    unsigned *cand = reinterpret_cast<unsigned *>(smax + D);    // [kTile]
+    unsigned *cand = reinterpret_cast<unsigned *>(PRUNE ? smax + D : wmax);  // [kTile]
     unsigned *hitmask = cand + kTile;                           // [kTile/32]
     unsigned *alive_w = hitmask + kTile / 32;                   // [kTile/32]   alive words of the tile
     unsigned *opened = alive_w + kTile / 32;                    // [NW] bins: bin already holds a pod (bit per node)
@@ -225,6 +225,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
     // fit no node of this stage now, hence - state only shrinks - none later in the tile either.  Pruning
     // earns time, never credit: the credited decisions are derived from the placements, not from the tests run.
     auto refresh_bounds = [&]() {
+        // bin stages, and node passes that fit the GPU in one wave: the placement chain is the critical path, not
+        // the scan, and the extra barrier per placing tile costs more than the pruning saves (measured)
+        if (!PRUNE) return;
         if (warp < n_warps) {
             const int n = (warp << 5) + lane;
 #pragma unroll
@@ -313,14 +316,14 @@ firstfit_pipeline_kernel(const PipelineParams p)
         const unsigned word = (tid < kTile && j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
         const bool is_alive = (word >> lane) & 1u;
         bool pass = is_alive;
-        if (is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
+        if (PRUNE && is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
 #pragma unroll
             for (int d = 0; d < D; ++d) pass = pass & (pre[d] <= smax[d]);
         }
-        const unsigned pword = __ballot_sync(0xFFFFFFFFu, pass);
+        const unsigned pword = PRUNE ? __ballot_sync(0xFFFFFFFFu, pass) : word;
         if (lane == 0 && warp < kTile / 32) {
             wcount[warp] = __popc(pword);
-            acount[warp] = __popc(word);
+            if (PRUNE) acount[warp] = __popc(word);
             alive_w[warp] = word;
         }
         if (tid < kTile / 32) hitmask[tid] = 0;
@@ -333,10 +336,11 @@ firstfit_pipeline_kernel(const PipelineParams p)
             const unsigned c = wcount[w];
             base += (w < warp) ? c : 0u;
             total += c;
-            alive_total += acount[w];
+            if (PRUNE) alive_total += acount[w];
         }
+        if (!PRUNE) alive_total = total;
         if (total == 0) {  // nothing alive, or nothing that could fit here: forward the tile untouched
-            forwarded += (long long)alive_total;
+            if (PRUNE) forwarded += (long long)alive_total;
             if (tid == 0) st_release(p.progress + stage, tile + 1);
             prefetch_row(tile + 1);
             continue;  // uniform: every thread sees the same total; (S1) protects the shared words
@@ -471,7 +475,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 // and thresholds only shrink while the tile is resolved).
                 double Mx[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) Mx[d] = wmax[warp * D + d];
+                for (int d = 0; d < D; ++d)
+                    Mx[d] = BINS ? warp_upper_bound(S[d])
+                                 : PRUNE ? wmax[warp * D + d] : warp_upper_bound(n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0);
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned ev_local = 0;
@@ -629,12 +635,6 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         if (BINS) opened[warp] = touched_or_open;
                         else dirty[warp] = touched_or_open;
                     }
-                    if (BINS && lane < D) {  // the bound this warp tightened after its last placing batch
-                        double b = Mx[0];
-#pragma unroll
-                        for (int d = 1; d < D; ++d) b = lane == d ? Mx[d] : b;
-                        wmax[warp * D + lane] = b;
-                    }
                 }
             }
             __syncthreads();
@@ -656,19 +656,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     thr_s[i] = node_threshold(cap_s[i], state_s[i]);
             }
         }
-        // node state changed: new bounds for the next tile (visible after its (S1)).  bins: every resolver warp
-        // has already stored the bound it kept tight while placing; nodes: from the refreshed thresholds.
-        if (n_placed_tile) {
-            if (BINS) {
-                if (tid < D) {
-                    double m = wmax[tid];
-                    for (int w = 1; w < n_warps; ++w) m = fmax(m, wmax[w * D + tid]);
-                    smax[tid] = m;
-                }
-            } else {
-                __syncthreads();  // thresholds just rewritten by all threads
-                refresh_bounds();
-            }
+        // node state changed: new bounds for the next tile (visible after its (S1))
+        if (PRUNE && n_placed_tile) {
+            __syncthreads();  // thresholds just rewritten by all threads
+            refresh_bounds();
         }
         ACSFIT_PROF(5)
 
