@@ -299,7 +299,7 @@ def run_ours(args):
         achieved = pipe_bytes / (pipe_ms * 1e-3) / 1e9 if pipe_ms > 0 else 0.0
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r01_pipeline_traffic.json")
-        if os.path.exists(prof):
+        if os.path.exists(prof) and args.config == "c2":  # the ncu capture is of the c2 workload
             try:
                 with open(prof) as f:
                     traffic = json.load(f).get("dram_bytes_per_launch")
@@ -328,6 +328,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "pipeline": {"stages": stats["stages"], "tiles": stats["tiles"]},
+            "pods_per_s": world * P / (dev_ms / args.steps * 1e-3),  # pending pods / tick time
         }
         if world == 1 and not args.no_cpu_baseline:
             if P * N <= 2 * 10 ** 9:
