@@ -93,7 +93,13 @@ ACSFIT_API const char *acsfit_last_error(const acsfit_ctx *ctx);
 ACSFIT_API acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx);
 ACSFIT_API acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx);
 /* pipeline tuning knobs (0 = library default): stages the node/bin axis is cut into at least,
- * and the watchdog in milliseconds */
+ * and the watchdog in milliseconds.
+ * Developer knobs read from the environment at acsfit_ctx_create (none changes a result, only the schedule):
+ *   ACSFIT_OVERLAP=0        do not chain the first bin pass behind the node pass on a second stream
+ *   ACSFIT_PRUNE=0|1        never / always use the scan-list-pruning instantiation of the node pass
+ *                           (default: only when the pass has more stages than the GPU holds at once)
+ *   ACSFIT_SMEM_FLOOR_KB=n  request at least n KB of shared memory per stage CTA (limits CTAs per SM)
+ *   ACSFIT_STREAM_BYTES=n   staging bytes per warp of the K1/K6 streaming kernels (2048 / 4096 / 8192) */
 ACSFIT_API acsfit_status acsfit_ctx_configure(acsfit_ctx *ctx, int min_stages, int watchdog_ms);
 /* when enabled, the first-fit / bin-pack pipeline launches are bracketed with CUDA events on the
  * launching stream (read back with acsfit_last_pipeline_stats) */
