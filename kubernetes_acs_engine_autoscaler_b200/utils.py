@@ -5,6 +5,7 @@ exactly (autoscaler/utils.py:6-74): a quantity is `float(digits) * multiplier`, 
 `digits / 1000`.  tests/golden/parse_vectors.json pins them against the reference.
 """
 import datetime
+import functools
 import re
 
 _DECIMAL = [('y', 1e-24), ('z', 1e-21), ('a', 1e-18), ('f', 1e-15), ('p', 1e-12), ('n', 1e-9), ('u', 1e-6),
@@ -16,8 +17,21 @@ SI_suffix = dict(_DECIMAL + _BINARY)
 SI_regex = re.compile(r"(\d+)(%s)?$" % "|".join(SI_suffix.keys()))
 
 
+@functools.lru_cache(maxsize=1 << 16)
+def _parse_SI_text(s):
+    match = SI_regex.match(s)
+    if match is None:
+        raise ValueError("Unknown SI quantity: %s" % s)
+    digits, suffix = match.groups()
+    return float(digits) * (SI_suffix[suffix] if suffix else 1.)
+
+
 def parse_SI(s):
-    """'1500m' -> 1500.0 * 1e-3 ; '3952Mi' -> 3952.0 * 2**20 ; raises ValueError otherwise."""
+    """'1500m' -> 1500.0 * 1e-3 ; '3952Mi' -> 3952.0 * 2**20 ; raises ValueError otherwise.
+    A cluster holds few distinct quantity strings, so exact `str` inputs are memoised (a pure function of the
+    text; errors are not cached and raise again); anything else takes the reference's route as is."""
+    if type(s) is str:
+        return _parse_SI_text(s)
     match = SI_regex.match(s)
     if match is None:
         raise ValueError("Unknown SI quantity: %s" % s)
