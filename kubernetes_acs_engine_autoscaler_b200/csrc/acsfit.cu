@@ -725,6 +725,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
     if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
     if (const char *env = getenv("ACSFIT_PRUNE")) ctx->prune = atoi(env);
+    if (const char *env = getenv("ACSFIT_MIN_STAGES")) ctx->min_stages = std::max(0, atoi(env));
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
