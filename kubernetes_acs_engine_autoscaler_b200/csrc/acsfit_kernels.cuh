@@ -563,13 +563,20 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
                         double r_next[D];
                         load_row<D>(r_next, brow + (size_t)(k + 1) * D);
-                        bool ok = true;
+                        // two independent and-chains over the dimensions (a chain of D dependent DSETPs sits on the
+                        // placement chain; halves combine with one PLOP3)
+                        bool ok = true, ok2 = true;
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
+                        for (int d = 0; d < D / 2; ++d) {
                             if (BINS) ok = ok & (r[d] <= S[d]);   // == (S - r >= 0) for finite values (scaler.py:139)
                             else ok = ok & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);  // kube.py:175
                         }
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+#pragma unroll
+                        for (int d = D / 2; d < D; ++d) {
+                            if (BINS) ok2 = ok2 & (r[d] <= S[d]);
+                            else ok2 = ok2 & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);
+                        }
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok & ok2);
                         if (m) {
                             if ((m & (0u - m)) == me) {  // the first fitting node of the warp takes the pod
 #pragma unroll
