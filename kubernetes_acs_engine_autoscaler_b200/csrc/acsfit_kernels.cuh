@@ -557,7 +557,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     const long long t_l0 = tracing ? clock64() : 0;
                     unsigned took = 0;    // bit k: dense entry k of the batch was placed by this warp
                     unsigned mymask = 0;  // bit k: ... by THIS lane's node
-                    const unsigned me = 1u << lane;
+                    const unsigned me = 1u << lane, le = (me << 1) - 1u;  // this lane's bit, and all bits up to it
                     for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
                     for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
@@ -576,9 +576,12 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             if (BINS) ok2 = ok2 & (r[d] <= S[d]);
                             else ok2 = ok2 & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);
                         }
+                        // two votes issued back to back: the predicate one steers the (uniform) branch without an
+                        // integer compare on the chain, the ballot names the first fitting node
+                        const bool any = __any_sync(0xFFFFFFFFu, ok & ok2);
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok & ok2);
-                        if (m) {
-                            if ((m & (0u - m)) == me) {  // the first fitting node of the warp takes the pod
+                        if (any) {
+                            if ((m & le) == me) {  // the first fitting node of the warp takes the pod
 #pragma unroll
                                 for (int d = 0; d < D; ++d)
                                     S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
