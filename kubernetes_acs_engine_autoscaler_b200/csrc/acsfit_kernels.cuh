@@ -16,9 +16,10 @@
 //     the tile-start state (pure DSETP work, pod rows broadcast from shared memory).  Because
 //     a node only ever fills up (requests are >= 0, rounding is monotone) a pod that fits no
 //     node of the stage under the tile-start state fits none later either: it is forwarded
-//     untouched.  The few pods that do hit are resolved by one warp strictly in pod order
-//     against the live thresholds (ballot + ffs over 32-node chunks), which is exactly the
-//     reference's loop restricted to this stage's nodes;
+//     untouched.  The few pods that do hit are resolved strictly in pod order by a chain of
+//     warps (warp w = nodes 32w..32w+31 of the stage, state in registers, the literal reference
+//     expression, one vote per entry), which is exactly the reference's loop restricted to this
+//     stage's nodes;
 //   * a pod that is placed has its alive bit cleared; pods still alive after the last stage
 //     are the pending pods (nodes) / flow into the next pass of fresh bins (bins).
 //
