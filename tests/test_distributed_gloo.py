@@ -85,6 +85,30 @@ def cluster_worker(rank, world, port, out_dir, n_blocks):
     D.shutdown()
 
 
+def test_three_rank_cluster_pipeline_with_tiny_blocks(tmp_path):
+    """uneven node ranges (301 nodes over 3 ranks), more blocks than some ranks ever see alive pods for"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    c, used0 = cluster_case()
+    feas_mask, _ = oracle.feasible_mask(c["req"], c["unit_all"])
+    rows = c["req"][np.nonzero(feas_mask)[0]]
+    used_ref = used0.copy()
+    placed_ref, calls_ref = oracle.first_fit_nodes(rows, c["cap_type"], c["node_type"], used_ref)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = os.path.join(str(tmp_path), "w3")
+    os.makedirs(out)
+    mp.spawn(cluster_worker, args=(3, port, out, 64), nprocs=3, join=True)
+    used_got = np.zeros_like(used0)
+    for rank in range(3):
+        z = np.load(os.path.join(out, "c%d.npz" % rank))
+        np.testing.assert_array_equal(z["placed"], placed_ref)
+        assert int(z["dec"][0]) == calls_ref
+        used_got[int(z["lo"]):int(z["hi"])] = z["used"]
+    assert used_got.tobytes() == used_ref.tobytes()
+
+
 def test_two_rank_cluster_pipeline_is_exact(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
