@@ -86,7 +86,14 @@ class KubePod(object):
         self.resources = KubeResource(pods=1, **totals)
 
     def _created_by(self):
-        return json.loads(self.annotations.get('kubernetes.io/created-by', '{}'))
+        """the created-by annotation, decoded (kube.py:51-58 decode it on every call; the text does not change
+        while a tick holds the object, so it is decoded once per text; a malformed annotation raises every time)"""
+        text = self.annotations.get('kubernetes.io/created-by', '{}')
+        cached = self.__dict__.get('_created_by_cache')
+        if cached is None or cached[0] is not text:
+            cached = (text, json.loads(text))
+            self.__dict__['_created_by_cache'] = cached
+        return cached[1]
 
     def is_mirrored(self):
         daemonset = self._created_by().get('reference', {}).get('kind') == 'DaemonSet'
