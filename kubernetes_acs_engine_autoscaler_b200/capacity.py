@@ -30,12 +30,7 @@ def load(path=None, cpu_reserve=None):
 
 
 data, RESOURCE_SPEC = OrderedDict(), {}
-try:
-    load()
-except FileNotFoundError:
-    # the reference fails at import here; we defer the failure to first use so that tools which
-    # only need the dense engine can import the package without a capacity file
-    pass
+load()  # like the reference (capacity.py:12-18): a missing table is an import-time error, not a KeyError later
 
 
 def get_capacity_for_instance_type(instance_type):

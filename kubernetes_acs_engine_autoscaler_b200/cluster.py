@@ -7,6 +7,7 @@ the kube adapter, then runs the whole decision path on the GPU:
 and hands the results back through the same calls the reference makes (scale_pools, the
 KubeNode mutators, the notifier).  `--dry-run` gates every side effect exactly as upstream.
 """
+import base64
 import logging
 import os
 import sys
@@ -21,6 +22,29 @@ from .kube import KubeNode, KubePod, KubePodStatus
 from .scaler import LOG_DETAIL_LIMIT
 
 logger = logging.getLogger('autoscaler.cluster')
+
+# inert stand-in for the certificate / key parameters an incremental agent-pool deployment never reads
+PLACEHOLDER_KEY = base64.b64encode(b"-----BEGIN CERTIFICATE-----\r\nacsfit placeholder, not a key\r\n"
+                                   b"-----END CERTIFICATE-----\r\n").decode("ascii")
+
+_pykube_ready = False
+
+
+def _pykube():
+    """import pykube once and apply the two process-wide settings the reference applies at import
+    (cluster.py:20-28): list pods of ALL namespaces (system pods count towards occupancy and may be
+    pending), and let urllib3 accept IP addresses in the API server certificate."""
+    global _pykube_ready
+    import pykube
+    if not _pykube_ready:
+        pykube.Pod.objects.namespace = None
+        try:
+            import backports.ssl_match_hostname as _bsm
+            pykube.http.requests.packages.urllib3.connection.match_hostname = _bsm.match_hostname
+        except (ImportError, AttributeError):  # python >= 3.7 ssl matches IP SANs natively
+            pass
+        _pykube_ready = True
+    return pykube
 
 
 class Cluster(object):
@@ -55,7 +79,7 @@ class Cluster(object):
 
     # ---- adapter boundary: cloud + kube clients (reference cluster.py:65-109) -----------------------
     def login(self):
-        import pykube
+        pykube = _pykube()
         adapters.call("login", self.service_principal_app_id, self.service_principal_secret,
                       self.service_principal_tenant_id, self.subscription_id)
         self.arm_template = adapters.call("download_template", self.resource_group, self.acs_deployment)
@@ -78,7 +102,9 @@ class Cluster(object):
         params['caPrivateKey'] = {'value': self.ca_private_key}
         params['servicePrincipalClientId'] = {'value': self.service_principal_app_id}
         params['servicePrincipalClientSecret'] = {'value': self.service_principal_secret}
-        placeholder = os.environ.get('ACSFIT_PLACEHOLDER_KEY', self.ca_private_key)
+        # never a real secret: a fixed, syntactically valid base64 blob (the reference sends an inert dummy
+        # certificate in these slots, cluster.py:97-106); $ACSFIT_PLACEHOLDER_KEY overrides it
+        placeholder = os.environ.get('ACSFIT_PLACEHOLDER_KEY', PLACEHOLDER_KEY)
         for key in ('kubeConfigPrivateKey', 'apiServerPrivateKey', 'etcdClientPrivateKey', 'etcdServerPrivateKey'):
             params[key] = {'value': placeholder}
         for i in range(5):
@@ -88,12 +114,10 @@ class Cluster(object):
         self.arm_template = adapters.call("delete_master_vm_extension", self.arm_template)
 
     def list_nodes(self):
-        import pykube
-        return pykube.Node.objects(self.api)
+        return _pykube().Node.objects(self.api)
 
     def list_pods(self):
-        import pykube
-        return pykube.Pod.objects(self.api)
+        return _pykube().Pod.objects(self.api)  # all namespaces, see _pykube()
 
     # ---- the tick ---------------------------------------------------------------------------------------
     def loop(self, debug):

@@ -17,5 +17,13 @@ class Config(object):
     pass
 
 
-Config.CAPACITY_DATA = _from_env('CAPACITY_DATA', 'data/capacity.json')
+def _default_capacity_data():
+    """the reference's default is the cwd-relative 'data/capacity.json' (config.py:5); when that file is not
+    there, the copy of the same constant table shipped at the root of this repository is used."""
+    if os.path.exists('data/capacity.json'):
+        return 'data/capacity.json'
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data', 'capacity.json')
+
+
+Config.CAPACITY_DATA = _from_env('CAPACITY_DATA', _default_capacity_data())
 Config.CAPACITY_CPU_RESERVE = _from_env('CAPACITY_CPU_RESERVE', 0.0, float)

@@ -11,7 +11,8 @@
  * (/root/reference/autoscaler, imported under oracle/ref_shim.py) on seeded
  * cluster states and on the reference's own known-answer tests
  * (test/test_cluster.py:56-73, test/test_scaler.py:53-77) and commits the
- * results under tests/golden/; tests/test_oracle_golden.py checks every
+ * results under tests/golden/; tests/test_host_golden_cpu.py (whole ticks replayed with this
+ * library as the engine) and tests/test_gpu_parity.py (CUDA vs this library) check every
  * function below against those vectors bit for bit.
  *
  * Every arithmetic expression keeps the reference's operation ORDER:
