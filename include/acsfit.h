@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ACSFIT_ABI_VERSION 1
+#define ACSFIT_ABI_VERSION 2
 #define ACSFIT_MAX_DIMS 16
 #define ACSFIT_MAX_POOLS 256
 
@@ -51,7 +51,8 @@ enum {
     ACSFIT_E_CUDA = -2,     /* a CUDA runtime call or kernel failed */
     ACSFIT_E_DOMAIN = -3,   /* input outside the reference's domain (negative / NaN request) */
     ACSFIT_E_TIMEOUT = -4,  /* device-side watchdog fired (inter-stage pipeline stalled) */
-    ACSFIT_E_NOMEM = -5
+    ACSFIT_E_NOMEM = -5,
+    ACSFIT_E_PEER = -6      /* cluster mode: a peer rank failed / did not arrive (in-stream barrier timed out) */
 };
 
 /* ClusterNodeState codes, in the order reference autoscaler/scaler.py:19-29 lists them */
@@ -101,8 +102,13 @@ ACSFIT_API acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx);
  *   ACSFIT_MIN_STAGES=n     same as acsfit_ctx_configure(min_stages) (default: one stage per SM; measured best
  *                           for the chained c2 tick as well: 148 -> 10.86 ms, 79 -> 11.13, 40 -> 11.4)
  *   ACSFIT_SMEM_FLOOR_KB=n  request at least n KB of shared memory per stage CTA (limits CTAs per SM)
- *   ACSFIT_STREAM_BYTES=n   staging bytes per warp of the K1/K6 streaming kernels (2048 / 4096 / 8192) */
+ *   ACSFIT_STREAM_BYTES=n   staging bytes per warp of the K1/K6 streaming kernels (2048 / 4096 / 8192)
+ *   ACSFIT_RANKS=0          never use the packed-rank scan (float64 compares instead; same results) */
 ACSFIT_API acsfit_status acsfit_ctx_configure(acsfit_ctx *ctx, int min_stages, int watchdog_ms);
+/* the same developer knobs by name, after ctx creation: "ranks" (0: float64 compare scan, 1: packed-rank scan when
+ * the tick's request table allows it -- the default), "prune", "overlap", "min_stages", "cluster_blocks" (cluster
+ * mode: cut the pod list of the node pass into this many blocks; 0 = automatic).  None changes a result. */
+ACSFIT_API acsfit_status acsfit_ctx_set_knob(acsfit_ctx *ctx, const char *name, int value);
 /* when enabled, the first-fit / bin-pack pipeline launches are bracketed with CUDA events on the
  * launching stream (read back with acsfit_last_pipeline_stats) */
 ACSFIT_API acsfit_status acsfit_ctx_set_timing(acsfit_ctx *ctx, int enabled);
@@ -257,6 +263,35 @@ ACSFIT_API acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *ro
                                    int64_t idle_threshold, const int64_t *budget0,
                                    const uint8_t *pool_scalable, int T, int dry_run,
                                    uint8_t *out_state, uint8_t *out_action);
+
+/*
+ * Cluster mode: ONE cluster (one pod list, one node list) on the `world` GPUs of one box, one process and one
+ * ctx per GPU.  The two sequential first-fit loops (reference cluster.py:184-204 and scaler.py:131-147) are
+ * parallel over the NODE (bin) axis, so rank r owns the r-th contiguous range of nodes (of every bin pass) and
+ * the pipeline of stages simply continues on the next GPU: stage 0 of rank r polls the progress counter of the
+ * last stage of rank r-1 and reads that rank's "still unplaced" bitmap, both through NVLink peer memory
+ * (CUDA IPC), tile by tile, inside the kernel.  Pods visit nodes in list order and every node sees the pods in
+ * list order, so placements, `used` bit patterns, pool sizes and the credited decisions are exactly those of
+ * the single-GPU call.  The only other exchanges are in-stream peer-memory barriers and element-wise merges of
+ * the placement vectors (each pod is placed by exactly one rank).
+ *
+ * Protocol: every rank calls acsfit_cluster_init, the 64-byte handles are all-gathered by the host layer
+ * (torch.distributed) and passed to acsfit_cluster_connect.  From then on acsfit_first_fit_nodes,
+ * acsfit_fulfill_pending, acsfit_scale_up and acsfit_scale_up_host must be called by ALL ranks with IDENTICAL
+ * arguments (replicated inputs); every rank returns the complete, identical result.
+ *   max_pods / max_nodes / max_dims size the exchange region this rank exports (cudaMalloc'ed by the library).
+ */
+#define ACSFIT_IPC_HANDLE_BYTES 64
+#define ACSFIT_MAX_RANKS 8
+ACSFIT_API acsfit_status acsfit_cluster_init(acsfit_ctx *ctx, int rank, int world, int64_t max_pods,
+                                             int64_t max_nodes, int max_dims, void *out_handle);
+/* all_handles [host]: world x ACSFIT_IPC_HANDLE_BYTES, rank-major (this rank's own entry included) */
+ACSFIT_API acsfit_status acsfit_cluster_connect(acsfit_ctx *ctx, const void *all_handles);
+/* in-stream barrier over the ranks (peer-memory flags); the first call must follow a host-level barrier */
+ACSFIT_API acsfit_status acsfit_cluster_barrier(acsfit_ctx *ctx, acsfit_stream_t stream);
+/* geometry of the last cluster-mode node pass: stage width, stages of this rank, pod blocks, resident stage CTAs */
+ACSFIT_API acsfit_status acsfit_cluster_last_plan(const acsfit_ctx *ctx, int *out_tn, int *out_stages,
+                                                  int *out_blocks, int *out_resident);
 
 /* number of kernels this ctx has launched so far (bench.py reports it as gpu_launches) */
 ACSFIT_API uint64_t acsfit_launch_count(const acsfit_ctx *ctx);

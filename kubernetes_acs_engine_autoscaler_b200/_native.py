@@ -6,9 +6,9 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libacsfit.so")
 
-OK, E_INVALID, E_CUDA, E_DOMAIN, E_TIMEOUT, E_NOMEM = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_DOMAIN, E_TIMEOUT, E_NOMEM, E_PEER = 0, -1, -2, -3, -4, -5, -6
 _STATUS_NAMES = {E_INVALID: "ACSFIT_E_INVALID", E_CUDA: "ACSFIT_E_CUDA", E_DOMAIN: "ACSFIT_E_DOMAIN",
-                 E_TIMEOUT: "ACSFIT_E_TIMEOUT", E_NOMEM: "ACSFIT_E_NOMEM"}
+                 E_TIMEOUT: "ACSFIT_E_TIMEOUT", E_NOMEM: "ACSFIT_E_NOMEM", E_PEER: "ACSFIT_E_PEER"}
 
 c_i64, c_int, c_vp, c_u64 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64
 
@@ -20,6 +20,7 @@ SIGNATURES = {
     "acsfit_ctx_destroy": (c_int, [c_vp]),
     "acsfit_ctx_configure": (c_int, [c_vp, c_int, c_int]),
     "acsfit_ctx_set_timing": (c_int, [c_vp, c_int]),
+    "acsfit_ctx_set_knob": (c_int, [c_vp, ctypes.c_char_p, c_int]),
     "acsfit_feasible_mask": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     "acsfit_occupancy": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "acsfit_first_fit_nodes": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -34,6 +35,10 @@ SIGNATURES = {
                                      c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acsfit_maintain_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
                                      c_i64, c_int, c_int, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "acsfit_cluster_init": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "acsfit_cluster_connect": (c_int, [c_vp, c_vp]),
+    "acsfit_cluster_barrier": (c_int, [c_vp, c_vp]),
+    "acsfit_cluster_last_plan": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acsfit_launch_count": (c_u64, [c_vp]),
     "acsfit_debug_profile": (c_int, [c_vp, c_int, c_vp, c_int, c_vp]),
     "acsfit_debug_trace": (c_int, [c_vp, c_int, c_vp, c_int]),

@@ -12,9 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "acsfit_kernels.cuh"
+#include "acsfit_rank.cuh"
 
 using namespace acsfit;
 
@@ -26,8 +29,20 @@ struct acsfit_ctx {
     int num_sms = 0;
     int min_stages = 0;       // 0 = number of SMs
     int watchdog_ms = 20000;
-    int resident_nodes[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // cached occupancy answers per D (full-size stages)
+    std::map<std::tuple<int, int, int, int, int>, int> resident_cache;  // (D, bins, prune, rank words, Tn) -> stage CTAs the GPU holds
     int prune = -1;           // -1: automatic (node passes that run in waves), 0 / 1: forced (ACSFIT_PRUNE)
+    int use_ranks = 1;        // packed-rank scan when the tick's distinct request values allow it (ACSFIT_RANKS=0: never)
+    RankLayout rk;            // rank tables of the current API call (rk.nw == 0: float64 scan)
+    // cluster mode (one cluster on `world` GPUs; see include/acsfit.h)
+    int rank = 0, world = 1;
+    unsigned char *xbase = nullptr;                     // this rank's exchange region (cudaMalloc, IPC-exported)
+    unsigned char *peer[ACSFIT_MAX_RANKS] = {nullptr};  // every rank's region as mapped here (peer[rank] == xbase)
+    size_t x_sync = 0, x_alive = 0, x_placed = 0, x_used = 0, x_bytes = 0;  // offsets inside a region
+    int64_t x_max_pods = 0, x_max_nodes = 0;
+    int x_max_dims = 0;
+    int epoch = 0;                                      // in-stream barrier count (same on every rank)
+    int force_blocks = 0;                               // developer knob "cluster_blocks"
+    int cl_tn = 0, cl_stages = 0, cl_blocks = 0, cl_resident = 0;  // geometry of the last cluster node pass
     int smem_floor_kb = 0;    // >0: request at least this much dynamic smem per stage CTA (limits CTAs per SM)
     char err[512] = {0};
     // grow-only device arena, bump-allocated per API call
@@ -725,6 +740,8 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     if (const char *env = getenv("ACSFIT_SMEM_FLOOR_KB")) ctx->smem_floor_kb = atoi(env);
     if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
     if (const char *env = getenv("ACSFIT_PRUNE")) ctx->prune = atoi(env);
+    if (const char *env = getenv("ACSFIT_RANKS")) ctx->use_ranks = atoi(env) != 0;
+    memset(&ctx->rk, 0, sizeof ctx->rk);
     if (const char *env = getenv("ACSFIT_MIN_STAGES")) ctx->min_stages = std::max(0, atoi(env));
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -757,6 +774,18 @@ extern "C" acsfit_status acsfit_ctx_configure(acsfit_ctx *ctx, int min_stages, i
     if (!ctx || min_stages < 0 || watchdog_ms < 0) return ACSFIT_E_INVALID;
     ctx->min_stages = min_stages;
     if (watchdog_ms) ctx->watchdog_ms = watchdog_ms;
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_ctx_set_knob(acsfit_ctx *ctx, const char *name, int value)
+{
+    if (!ctx || !name) return ACSFIT_E_INVALID;
+    if (!strcmp(name, "ranks")) ctx->use_ranks = value != 0;
+    else if (!strcmp(name, "prune")) ctx->prune = value;
+    else if (!strcmp(name, "overlap")) ctx->overlap = value != 0;
+    else if (!strcmp(name, "min_stages")) ctx->min_stages = std::max(0, value);
+    else if (!strcmp(name, "cluster_blocks")) ctx->force_blocks = std::max(0, value);
+    else return fail(ctx, ACSFIT_E_INVALID, "unknown knob %s", name);
     return ACSFIT_OK;
 }
 
@@ -828,6 +857,7 @@ static acsfit_status enter(acsfit_ctx *ctx, int D)
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(ctx, ACSFIT_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     ctx->arena_off = 0;
+    ctx->rk.nw = 0;  // rank tables live in the arena of one API call
     return ACSFIT_OK;
 }
 
@@ -863,6 +893,74 @@ static acsfit_status compact(acsfit_ctx *ctx, Pred pred, int64_t n, const int32_
     return ACSFIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// rank tables of the packed-rank scan (acsfit_rank.cuh).  On success ctx->rk describes the layout; when a
+// dimension has too many distinct values, or the fields need more than 128 bits, ctx->rk.nw stays 0 and the
+// pipelines run their float64 compare scan.  Scratch comes from the arena of the current API call.
+// ---------------------------------------------------------------------------------------------
+static size_t rank_scratch(int64_t rows, int D)
+{
+    return (size_t)D * kRankSlots * (sizeof(unsigned long long) + sizeof(unsigned short)) +
+           (size_t)D * kRankCap * sizeof(double) + sizeof(uint32_t) * 4 * (size_t)std::max<int64_t>(rows, 1) + 16 * 256;
+}
+
+static acsfit_status build_ranks(acsfit_ctx *ctx, const double *req, int64_t rows, int D, cudaStream_t st)
+{
+    ctx->rk.nw = 0;
+    if (!ctx->use_ranks || rows <= 0) return ACSFIT_OK;
+    TAKE(keys, unsigned long long, (size_t)D * kRankSlots);
+    TAKE(ranks, unsigned short, (size_t)D * kRankSlots);
+    TAKE(sorted, double, (size_t)D * kRankCap);
+    TAKE(counts, int, 16);
+    TAKE(packed, uint32_t, 4 * (size_t)rows);
+    CUDA_TRY(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * (size_t)D * kRankSlots, st));
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * 16, st));
+    rank_insert_kernel<<<grid_for(ctx, rows * D, 256), 256, 0, st>>>(req, rows, D, keys, counts);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(rank_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned long long) * kRankCap)));
+        attr_set = true;
+    }
+    rank_sort_kernel<<<D, 1024, sizeof(unsigned long long) * kRankCap, st>>>(keys, counts, sorted, ranks);
+    ctx->launches += 2;
+    int U[16];
+    CUDA_TRY(cudaMemcpyAsync(U, counts, sizeof(int) * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    // field layout: dimension d needs bitlen(U_d) bits for t' in [0, U_d] plus one guard bit; fields are placed
+    // in dimension order and never straddle a 32-bit word
+    RankLayout rk;
+    memset(&rk, 0, sizeof rk);
+    RankFields f;
+    memset(&f, 0, sizeof f);
+    int word = 0, used = 0;
+    for (int d = 0; d < D; ++d) {
+        if (U[d] > kRankCap || U[d] < 1) return ACSFIT_OK;  // too many distinct values: float64 scan
+        int bits = 0;
+        while ((1 << bits) <= U[d]) ++bits;
+        if (used + bits + 1 > 32) {
+            ++word;
+            used = 0;
+        }
+        if (word >= 4) return ACSFIT_OK;  // does not fit 128 bits: float64 scan
+        rk.word[d] = f.word[d] = (uint8_t)word;
+        rk.shift[d] = f.shift[d] = (uint8_t)used;
+        rk.guard[word] |= 1u << (used + bits);
+        rk.count[d] = U[d];
+        used += bits + 1;
+    }
+    const int nw = word + 1 == 3 ? 4 : word + 1;
+    rank_pack_kernel<<<grid_for(ctx, rows, 256), 256, 0, st>>>(req, rows, D, keys, ranks, f, nw, packed);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    rk.nw = nw;
+    rk.sorted = sorted;
+    rk.packed = packed;
+    ctx->rk = rk;
+    return ACSFIT_OK;
+}
+
 struct StagePlan {
     int Tn, NS, stages;
 };
@@ -872,7 +970,7 @@ struct StagePlan {
 static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_stages, int D, bool bins)
 {
     const int want = ctx->min_stages > 0 ? ctx->min_stages : ctx->num_sms;  // one stage per SM measured best
-    const int K = nodes_per_thread(D);
+    const int K = nodes_per_thread(D, ctx->rk.nw);
     int NS = max_stage_nodes(D, bins) / K;
     while (NS > 1 && (n_nodes + (int64_t)NS * K - 1) / ((int64_t)NS * K) < want) NS >>= 1;
     StagePlan p;
@@ -885,20 +983,26 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
     return p;
 }
 
-template <int D, bool BINS, bool PRUNE>
-static acsfit_status launch_pipeline_v(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
+template <int D, bool BINS, bool PRUNE, int RW>
+static acsfit_status launch_pipeline_w(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
 {
     constexpr int NT = stage_threads(D, BINS);
-    size_t smem = PipelineSmem<D, BINS, NT, PRUNE>::bytes(pp.Tn);
+    size_t smem = PipelineSmem<D, BINS, NT, PRUNE, RW>::bytes(pp.Tn);
     if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
-    auto kern = firstfit_pipeline_kernel<D, BINS, NT, PRUNE>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (resident) {  // only asked: how many stages does the GPU hold at once?
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-        *resident = per_sm * ctx->num_sms;
+    auto kern = firstfit_pipeline_kernel<D, BINS, NT, PRUNE, RW>;
+    if (resident) {  // only asked: how many stages does the GPU hold at once?  (cached: the query costs ~10 us)
+        const auto key = std::make_tuple(D, (int)BINS, (int)PRUNE, RW, pp.Tn);
+        auto it = ctx->resident_cache.find(key);
+        if (it == ctx->resident_cache.end()) {
+            int per_sm = 0;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+            it = ctx->resident_cache.emplace(key, per_sm * ctx->num_sms).first;
+        }
+        *resident = it->second;
         return ACSFIT_OK;
     }
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PipelineParams q = pp;
     q.prof = (ctx->prof_dev && stages <= kProfStages) ? ctx->prof_dev : nullptr;
     if (q.prof) {
@@ -913,6 +1017,19 @@ static acsfit_status launch_pipeline_v(acsfit_ctx *ctx, const PipelineParams &pp
     return ACSFIT_OK;
 }
 
+// the instantiation is chosen by the rank layout of the call: 0 (float64 scan), 1, 2 or 4 packed words per row
+template <int D, bool BINS, bool PRUNE>
+static acsfit_status launch_pipeline_v(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
+{
+    switch (pp.rk.nw) {
+    case 0: return launch_pipeline_w<D, BINS, PRUNE, 0>(ctx, pp, stages, st, resident);
+    case 1: return launch_pipeline_w<D, BINS, PRUNE, 1>(ctx, pp, stages, st, resident);
+    case 2: return launch_pipeline_w<D, BINS, PRUNE, 2>(ctx, pp, stages, st, resident);
+    case 4: return launch_pipeline_w<D, BINS, PRUNE, 4>(ctx, pp, stages, st, resident);
+    default: return fail(ctx, ACSFIT_E_INVALID, "rank layout with %d words", pp.rk.nw);
+    }
+}
+
 template <int D, bool BINS>
 static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st)
 {
@@ -923,9 +1040,8 @@ static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp
         // c2 tick 10.75 -> 10.93 ms).  ACSFIT_PRUNE=0/1 forces either.
         int prune = ctx->prune;
         if (prune < 0) {
-            int &resident = ctx->resident_nodes[D == 2 ? 0 : D == 4 ? 1 : D == 8 ? 2 : 3][pp.Tn == max_stage_nodes(D, false) ? 0 : 1];
-            if (resident <= 0 || pp.Tn != max_stage_nodes(D, false))  // asked once per shape (the query costs ~10 us)
-                TRY((launch_pipeline_v<D, BINS, false>(ctx, pp, stages, st, &resident)));
+            int resident = 0;
+            TRY((launch_pipeline_v<D, BINS, false>(ctx, pp, stages, st, &resident)));
             prune = stages > resident;
         }
         if (prune) return launch_pipeline_v<D, false, true>(ctx, pp, stages, st, nullptr);
@@ -955,6 +1071,391 @@ static acsfit_status check_pipeline_status(acsfit_ctx *ctx, const int *status_de
     return ACSFIT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// cluster mode: one cluster on the GPUs of one box (include/acsfit.h).  Exchange region of a rank:
+//   [0, 1024)   header: arrive[ACSFIT_MAX_RANKS] ints (barrier flags, slot r written by rank r), status int at
+//               +64, 16 uint64 scalars at +128
+//   x_sync      kClusterBlocks sync sets of kClusterSyncInts ints (ticket, status, drained, ..., progress[stages])
+//   x_alive     "still unplaced" bitmap of the running pass (read by the next rank's stage 0)
+//   x_placed    this rank's placements of the running pass (merged element-wise by every rank)
+//   x_used      this rank's node rows after the node pass (gathered by every rank)
+// ---------------------------------------------------------------------------------------------
+constexpr int kClusterBlocks = 64;
+constexpr int kClusterSyncInts = 8 + 4096;
+constexpr size_t kClusterHdr = 1024;
+
+namespace {
+struct PeerInts { int *p[ACSFIT_MAX_RANKS]; };
+struct PeerI32 { const int32_t *p[ACSFIT_MAX_RANKS]; };
+struct PeerF64 { const double *p[ACSFIT_MAX_RANKS]; };
+struct PeerU64 { const unsigned long long *p[ACSFIT_MAX_RANKS]; };
+struct RangeTable { int64_t lo[ACSFIT_MAX_RANKS + 1]; };
+
+// every rank tells every rank "I am at barrier `epoch`", then waits until all have said so.  The flags are
+// written and polled with system scope (they live in peer memory); kernels that ran before this one on the
+// stream have completed, so their global writes are visible to whoever passes the barrier.
+__global__ void cluster_barrier_kernel(PeerInts arrive, int rank, int world, int epoch, int *status,
+                                       unsigned long long timeout_ns)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    st_release_sys(arrive.p[r] + rank, epoch);
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(arrive.p[rank] + r) < epoch) {
+        if ((++spins & 255u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+            atomicExch(status, 3);
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+
+// element-wise maximum over the ranks' vectors (each pod is placed by at most one rank, the others hold -1)
+__global__ void merge_max_i32_kernel(PeerI32 src, int world, int64_t n, int32_t *out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t m = __ldcg(src.p[0] + i);
+        for (int r = 1; r < world; ++r) m = max(m, __ldcg(src.p[r] + i));
+        out[i] = m;
+    }
+}
+
+// used[n] of every node from the rank that owns it (rows are stored at their GLOBAL position in x_used)
+__global__ void gather_rows_kernel(PeerF64 src, RangeTable rt, int world, int rank, int64_t N, int D, double *used)
+{
+    const int64_t total = N * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / D;
+        int r = 0;
+        while (r + 1 < world && n >= rt.lo[r + 1]) ++r;
+        if (r != rank) used[i] = __ldcg(src.p[r] + i);
+    }
+}
+
+// out[k] = sum over ranks of scalars_r[k] (k < 8), out[8 + k] = max over ranks of scalars_r[k]; out[16] = max status
+__global__ void cluster_scalars_kernel(PeerU64 scal, PeerInts status, int world, unsigned long long *out)
+{
+    const int k = threadIdx.x;
+    if (k < 8) {
+        unsigned long long sum = 0, mx = 0;
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long v = __ldcg(scal.p[r] + k);
+            sum += v;
+            mx = v > mx ? v : mx;
+        }
+        out[k] = sum;
+        out[8 + k] = mx;
+    }
+    if (k == 8) {
+        int m = 0;
+        for (int r = 0; r < world; ++r) m = max(m, __ldcg(status.p[r]));
+        out[16] = (unsigned long long)m;
+    }
+}
+}  // namespace
+
+static int *x_arrive(const acsfit_ctx *ctx, int r) { return reinterpret_cast<int *>(ctx->peer[r]); }
+static int *x_status(const acsfit_ctx *ctx, int r) { return reinterpret_cast<int *>(ctx->peer[r] + 64); }
+static unsigned long long *x_scalars(const acsfit_ctx *ctx, int r) { return reinterpret_cast<unsigned long long *>(ctx->peer[r] + 128); }
+static int *x_syncset(const acsfit_ctx *ctx, int r, int b) { return reinterpret_cast<int *>(ctx->peer[r] + ctx->x_sync) + (size_t)b * kClusterSyncInts; }
+static uint32_t *x_alive_of(const acsfit_ctx *ctx, int r) { return reinterpret_cast<uint32_t *>(ctx->peer[r] + ctx->x_alive); }
+static int32_t *x_placed_of(const acsfit_ctx *ctx, int r) { return reinterpret_cast<int32_t *>(ctx->peer[r] + ctx->x_placed); }
+static double *x_used_of(const acsfit_ctx *ctx, int r) { return reinterpret_cast<double *>(ctx->peer[r] + ctx->x_used); }
+
+static acsfit_status cluster_barrier(acsfit_ctx *ctx, cudaStream_t st)
+{
+    PeerInts a;
+    for (int r = 0; r < ACSFIT_MAX_RANKS; ++r) a.p[r] = r < ctx->world ? x_arrive(ctx, r) : nullptr;
+    ++ctx->epoch;
+    cluster_barrier_kernel<<<1, 32, 0, st>>>(a, ctx->rank, ctx->world, ctx->epoch, x_status(ctx, ctx->rank),
+                                             (unsigned long long)ctx->watchdog_ms * 1000000ull);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+// out[i] = max over the ranks of their x_placed[i]; bracketed by the two barriers that make the vectors final
+// before they are read and keep them untouched until every rank has read them
+static acsfit_status cluster_merge_placed(acsfit_ctx *ctx, int64_t n, int32_t *out, cudaStream_t st)
+{
+    TRY(cluster_barrier(ctx, st));
+    PeerI32 src;
+    for (int r = 0; r < ACSFIT_MAX_RANKS; ++r) src.p[r] = r < ctx->world ? x_placed_of(ctx, r) : nullptr;
+    if (n > 0) {
+        merge_max_i32_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(src, ctx->world, n, out);
+        ++ctx->launches;
+    }
+    TRY(cluster_barrier(ctx, st));
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
+// sums one device-side uint64 over the ranks (e.g. the credited bin tests each rank counted) and returns the
+// highest pipeline status any rank recorded; synchronises the stream
+static acsfit_status cluster_sum_u64(acsfit_ctx *ctx, const unsigned long long *value_dev, unsigned long long *scratch17_dev,
+                                     unsigned long long *out_sum, cudaStream_t st)
+{
+    if (value_dev)
+        CUDA_TRY(cudaMemcpyAsync(x_scalars(ctx, ctx->rank), value_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    else
+        CUDA_TRY(cudaMemsetAsync(x_scalars(ctx, ctx->rank), 0, sizeof(unsigned long long), st));
+    TRY(cluster_barrier(ctx, st));
+    PeerU64 sc;
+    PeerInts stw;
+    for (int r = 0; r < ACSFIT_MAX_RANKS; ++r) {
+        sc.p[r] = r < ctx->world ? x_scalars(ctx, r) : nullptr;
+        stw.p[r] = r < ctx->world ? x_status(ctx, r) : nullptr;
+    }
+    cluster_scalars_kernel<<<1, 32, 0, st>>>(sc, stw, ctx->world, scratch17_dev);
+    ++ctx->launches;
+    TRY(cluster_barrier(ctx, st));
+    unsigned long long h[17];
+    CUDA_TRY(cudaMemcpyAsync(h, scratch17_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    if (out_sum) *out_sum = h[0];
+    if (h[16] == 3) return fail(ctx, ACSFIT_E_PEER, "cluster barrier timed out: a peer rank did not arrive");
+    if (h[16] != 0) return fail(ctx, ACSFIT_E_TIMEOUT, "first-fit pipeline watchdog fired on some rank");
+    return ACSFIT_OK;
+}
+
+// first node of rank r's range
+static int64_t cluster_lo(int64_t N, int world, int r) { return N * r / world; }
+
+extern "C" acsfit_status acsfit_cluster_init(acsfit_ctx *ctx, int rank, int world, int64_t max_pods, int64_t max_nodes,
+                                             int max_dims, void *out_handle)
+{
+    if (!ctx || !out_handle || world < 1 || world > ACSFIT_MAX_RANKS || rank < 0 || rank >= world || max_pods < 0 ||
+        max_nodes < 0 || max_dims < 1 || max_dims > ACSFIT_MAX_DIMS)
+        return fail(ctx, ACSFIT_E_INVALID, "cluster_init: bad arguments");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->xbase) return fail(ctx, ACSFIT_E_INVALID, "cluster_init: already initialised");
+    ctx->x_sync = kClusterHdr;
+    ctx->x_alive = align_up(ctx->x_sync + sizeof(int) * (size_t)kClusterBlocks * kClusterSyncInts, 256);
+    ctx->x_placed = align_up(ctx->x_alive + sizeof(uint32_t) * (size_t)((max_pods + 31) / 32 + 8), 256);
+    ctx->x_used = align_up(ctx->x_placed + sizeof(int32_t) * (size_t)(max_pods + 8), 256);
+    ctx->x_bytes = align_up(ctx->x_used + sizeof(double) * (size_t)(max_nodes + 1) * max_dims, 1 << 20);
+    CUDA_TRY(cudaMalloc(&ctx->xbase, ctx->x_bytes));
+    CUDA_TRY(cudaMemset(ctx->xbase, 0, ctx->x_bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == ACSFIT_IPC_HANDLE_BYTES, "IPC handle size");
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->xbase));
+    memcpy(out_handle, &h, sizeof h);
+    ctx->rank = rank;
+    ctx->world = 1;  // becomes `world` in cluster_connect
+    ctx->x_max_pods = max_pods;
+    ctx->x_max_nodes = max_nodes;
+    ctx->x_max_dims = max_dims;
+    ctx->epoch = 0;
+    ctx->peer[rank] = ctx->xbase;
+    ctx->cl_tn = -world;  // remembered until connect
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_cluster_connect(acsfit_ctx *ctx, const void *all_handles)
+{
+    if (!ctx || !all_handles || !ctx->xbase || ctx->cl_tn >= 0) return fail(ctx, ACSFIT_E_INVALID, "cluster_connect: call cluster_init first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int world = -ctx->cl_tn;
+    const unsigned char *hs = static_cast<const unsigned char *>(all_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == ctx->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * ACSFIT_IPC_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer[r] = static_cast<unsigned char *>(ptr);
+    }
+    ctx->world = world;
+    ctx->cl_tn = 0;
+    if (ctx->watchdog_ms < 60000) ctx->watchdog_ms = 60000;  // a rank legitimately waits for all the ranks before it
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_cluster_barrier(acsfit_ctx *ctx, acsfit_stream_t stream)
+{
+    if (!ctx || ctx->world < 2) return fail(ctx, ACSFIT_E_INVALID, "cluster_barrier: not in cluster mode");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    TRY(cluster_barrier(ctx, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int status = 0;
+    CUDA_TRY(cudaMemcpy(&status, x_status(ctx, ctx->rank), sizeof status, cudaMemcpyDeviceToHost));
+    if (status) return fail(ctx, ACSFIT_E_PEER, "cluster barrier timed out");
+    return ACSFIT_OK;
+}
+
+extern "C" acsfit_status acsfit_cluster_last_plan(const acsfit_ctx *ctx, int *out_tn, int *out_stages, int *out_blocks,
+                                                  int *out_resident)
+{
+    if (!ctx) return ACSFIT_E_INVALID;
+    if (out_tn) *out_tn = ctx->cl_tn;
+    if (out_stages) *out_stages = ctx->cl_stages;
+    if (out_blocks) *out_blocks = ctx->cl_blocks;
+    if (out_resident) *out_resident = ctx->cl_resident;
+    return ACSFIT_OK;
+}
+
+// stage CTAs of one pipeline instantiation the GPU holds at once (D, mode and rank layout of the current call)
+static int resident_stages(acsfit_ctx *ctx, int D, bool bins, int Tn)
+{
+    PipelineParams q;
+    memset(&q, 0, sizeof q);
+    q.Tn = Tn;
+    q.rk = ctx->rk;
+    int resident = 0;
+    acsfit_status s = ACSFIT_E_INVALID;
+    switch (D) {
+    case 2: s = bins ? launch_pipeline_v<2, true, false>(ctx, q, 0, nullptr, &resident) : launch_pipeline_v<2, false, false>(ctx, q, 0, nullptr, &resident); break;
+    case 4: s = bins ? launch_pipeline_v<4, true, false>(ctx, q, 0, nullptr, &resident) : launch_pipeline_v<4, false, false>(ctx, q, 0, nullptr, &resident); break;
+    case 8: s = bins ? launch_pipeline_v<8, true, false>(ctx, q, 0, nullptr, &resident) : launch_pipeline_v<8, false, false>(ctx, q, 0, nullptr, &resident); break;
+    case 16: s = bins ? launch_pipeline_v<16, true, false>(ctx, q, 0, nullptr, &resident) : launch_pipeline_v<16, false, false>(ctx, q, 0, nullptr, &resident); break;
+    default: break;
+    }
+    return s == ACSFIT_OK ? resident : 0;
+}
+
+// Cluster.get_pending_pods for one cluster on all ranks (include/acsfit.h, "Cluster mode").  Inputs are
+// replicated; rank r fits the pods that reach it onto nodes [lo_r, lo_{r+1}).  When a rank's stages fit the GPU
+// at once the whole pod list is one launch per rank and the ranks overlap tile by tile; otherwise (waves) the
+// list is cut into pod blocks, one launch per block and rank, and the ranks overlap block by block.
+// On return placed_out[F] and used[N, D] are complete and identical on every rank.
+static acsfit_status cluster_first_fit(acsfit_ctx *ctx, const double *req, const int32_t *list_f, int64_t F, int D,
+                                       const double *cap_type, const int32_t *node_type, double *used, int64_t N,
+                                       int32_t *placed_out, unsigned long long *decisions_dev, cudaStream_t st)
+{
+    const int W = ctx->world, rank = ctx->rank;
+    if (decisions_dev) CUDA_TRY(cudaMemsetAsync(decisions_dev, 0, sizeof(unsigned long long), st));
+    if (F == 0) return ACSFIT_OK;
+    if (F > ctx->x_max_pods || N > ctx->x_max_nodes || D > ctx->x_max_dims)
+        return fail(ctx, ACSFIT_E_INVALID, "cluster mode: %lld pods / %lld nodes / %d dims exceed the exchange region "
+                    "(cluster_init: %lld / %lld / %d)", (long long)F, (long long)N, D, (long long)ctx->x_max_pods,
+                    (long long)ctx->x_max_nodes, ctx->x_max_dims);
+    fill_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(placed_out, F, -1);
+    ++ctx->launches;
+    if (N == 0) {
+        CUDA_TRY(cudaGetLastError());
+        return ACSFIT_OK;
+    }
+    // geometry, identical on every rank: the narrowest stage (>= 32 nodes) whose stage count still fits the GPU
+    // at once for the largest node range; the full width and pod blocks when even that runs in waves
+    int64_t n_max = 0;
+    for (int r = 0; r < W; ++r) n_max = std::max(n_max, cluster_lo(N, W, r + 1) - cluster_lo(N, W, r));
+    const int K = nodes_per_thread(D, ctx->rk.nw);
+    const int tn_max = max_stage_nodes(D, false);
+    int Tn = tn_max, resident = resident_stages(ctx, D, false, tn_max);
+    for (int t = std::max(32, K); t <= tn_max; t <<= 1) {
+        const int res = resident_stages(ctx, D, false, t);
+        if (res > 0 && (n_max + t - 1) / t <= res) {
+            Tn = t;
+            resident = res;
+            break;
+        }
+    }
+    if (resident <= 0) return fail(ctx, ACSFIT_E_CUDA, "cluster mode: occupancy query failed");
+    const int64_t stages_max = (n_max + Tn - 1) / Tn;
+    if (stages_max + 8 > kClusterSyncInts) return fail(ctx, ACSFIT_E_INVALID, "cluster mode: %lld stages per rank", (long long)stages_max);
+    const int tiles = (int)((F + kTile - 1) / kTile);
+    int blocks = 1, tpb = tiles;
+    if (stages_max > resident || ctx->force_blocks > 0) {
+        blocks = std::min(kClusterBlocks, std::max(1, std::min(tiles, ctx->force_blocks > 0 ? ctx->force_blocks : 4 * W)));
+        tpb = (tiles + blocks - 1) / blocks;
+        blocks = (tiles + tpb - 1) / tpb;
+    }
+    const int64_t lo = cluster_lo(N, W, rank), hi = cluster_lo(N, W, rank + 1);
+    const int my_stages = (int)std::max<int64_t>(1, (hi - lo + Tn - 1) / Tn);
+    int up_stages = 0;
+    if (rank > 0) up_stages = (int)std::max<int64_t>(1, (lo - cluster_lo(N, W, rank - 1) + Tn - 1) / Tn);
+    ctx->cl_tn = Tn;
+    ctx->cl_stages = my_stages;
+    ctx->cl_blocks = blocks;
+    ctx->cl_resident = resident;
+
+    uint32_t *alive = x_alive_of(ctx, rank);
+    int32_t *placed_x = x_placed_of(ctx, rank);
+    CUDA_TRY(cudaMemsetAsync(x_status(ctx, rank), 0, sizeof(int), st));  // (peers read it only between barriers)
+    CUDA_TRY(cudaMemsetAsync(x_syncset(ctx, rank, 0), 0, sizeof(int) * (size_t)blocks * kClusterSyncInts, st));
+    fill_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(placed_x, F, -1);
+    if (rank == 0) fill_alive_kernel<<<grid_for(ctx, (F + 31) / 32, 256), 256, 0, st>>>(alive, F);
+    ctx->launches += 2;
+    TRY(cluster_barrier(ctx, st));  // every rank's counters are zero before anybody polls them
+
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    for (int b = 0; b < blocks; ++b) {
+        PipelineParams pp;
+        memset(&pp, 0, sizeof pp);
+        int *sync = x_syncset(ctx, rank, b);
+        pp.req = req;
+        pp.pod_idx = list_f;
+        pp.M = F;
+        pp.alive = alive;
+        pp.placed = placed_x;
+        pp.cap_type = cap_type;
+        pp.node_type = node_type;
+        pp.used = used;
+        pp.node_lo = lo;
+        pp.node_hi = hi;
+        pp.Tn = Tn;
+        pp.NS = Tn / K;
+        pp.tile_lo = b * tpb;
+        pp.num_tiles = std::min(tpb, tiles - b * tpb);
+        pp.ticket = sync;
+        pp.status = x_status(ctx, rank);  // one abort word per rank
+        pp.drained = sync + 2;
+        pp.progress = sync + 8;
+        pp.sys_scope = 1;
+        if (rank > 0) {
+            pp.upstream = x_syncset(ctx, rank - 1, b) + 8 + (up_stages - 1);
+            pp.alive_in = x_alive_of(ctx, rank - 1);
+        }
+        pp.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+        pp.rk = ctx->rk;
+        TRY(launch_pipeline<false>(ctx, D, pp, my_stages, st));
+    }
+    if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+    // this rank's node rows, at their global position, for the other ranks to fetch
+    if (hi > lo)
+        CUDA_TRY(cudaMemcpyAsync(x_used_of(ctx, rank) + (size_t)lo * D, used + (size_t)lo * D,
+                                 sizeof(double) * (size_t)(hi - lo) * D, cudaMemcpyDeviceToDevice, st));
+    TRY(cluster_barrier(ctx, st));
+    {
+        PeerI32 src;
+        PeerF64 us;
+        RangeTable rt;
+        for (int r = 0; r < ACSFIT_MAX_RANKS; ++r) {
+            src.p[r] = r < W ? x_placed_of(ctx, r) : nullptr;
+            us.p[r] = r < W ? x_used_of(ctx, r) : nullptr;
+        }
+        for (int r = 0; r <= ACSFIT_MAX_RANKS; ++r) rt.lo[r] = cluster_lo(N, W, std::min(r, W));
+        merge_max_i32_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(src, W, F, placed_out);
+        gather_rows_kernel<<<grid_for(ctx, N * D, 256), 256, 0, st>>>(us, rt, W, rank, N, D, used);
+        ctx->launches += 2;
+    }
+    TRY(cluster_barrier(ctx, st));
+    if (decisions_dev) {
+        decisions_kernel<<<grid_for(ctx, F, 256), 256, 0, st>>>(placed_out, F, N, decisions_dev);
+        ++ctx->launches;
+    }
+    TAKE(sc17, unsigned long long, 17);
+    TRY(cluster_sum_u64(ctx, nullptr, sc17, nullptr, st));  // status of all ranks (synchronises)
+    ctx->last_stages += my_stages * blocks;
+    ctx->last_tiles += tiles;
+    if (ctx->timing) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms += ms;
+        if (decisions_dev) {
+            unsigned long long d = 0;
+            CUDA_TRY(cudaMemcpy(&d, decisions_dev, sizeof d, cudaMemcpyDeviceToHost));
+            ctx->last_decisions += d;
+        }
+    }
+    return ACSFIT_OK;
+}
+
 static void reset_stats(acsfit_ctx *ctx)
 {
     ctx->last_ms = 0.0;
@@ -967,14 +1468,17 @@ static void reset_stats(acsfit_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 static size_t first_fit_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N)
 {
-    const StagePlan plan = plan_stages(ctx, std::max<int64_t>(N, 1), 0, 16, false);
-    return 8192 + sizeof(uint32_t) * (size_t)((P + 31) / 32) + sizeof(int) * ((size_t)plan.stages + 8);
+    // stages: whatever plan_stages picks for any D / rank layout stays below this bound
+    const size_t stages = (size_t)std::max<int64_t>(4 * std::max(ctx->min_stages, ctx->num_sms), N / 16 + 2);
+    return 8192 + sizeof(uint32_t) * (size_t)((P + 31) / 32) + sizeof(int) * (stages + 8);
 }
 
 static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const int32_t *pod_idx, int64_t P, int D,
                                     const double *cap_type, const int32_t *node_type, double *used, int64_t N,
                                     int32_t *out_placed, unsigned long long *out_decisions, cudaStream_t st)
 {
+    if (ctx->world > 1)
+        return cluster_first_fit(ctx, req, pod_idx, P, D, cap_type, node_type, used, N, out_placed, out_decisions, st);
     if (out_decisions) CUDA_TRY(cudaMemsetAsync(out_decisions, 0, sizeof(unsigned long long), st));
     if (P == 0) return ACSFIT_OK;
     fill_i32_kernel<<<grid_for(ctx, P, 256), 256, 0, st>>>(out_placed, P, -1);
@@ -1012,6 +1516,7 @@ static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const in
     pp.status = status;
     pp.drained = drained;
     pp.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+    pp.rk = ctx->rk;
 
     if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
     TRY(launch_pipeline<false>(ctx, D, pp, plan.stages, st));
@@ -1082,7 +1587,6 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
     TAKE(evals_dev, unsigned long long, 1);
     TAKE(count_dev, unsigned long long, 1);
     TAKE(max_bin_dev, int, 1);
-    int *ticket = sync_words, *status = sync_words + 1, *drained = sync_words + 2, *progress = sync_words + 8;
 
     if (T > 0) CUDA_TRY(cudaMemcpyAsync(unit_dev, unit_host, sizeof(double) * T * D, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(evals_dev, 0, sizeof(unsigned long long), st));
@@ -1132,39 +1636,74 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
                 ++ctx->launches;
             }
             while (M > 0) {
-                const StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D, true);  // at most one bin per pod
-                CUDA_TRY(cudaMemsetAsync(sync_words, 0, sizeof(int) * (plan.stages + 8), st));
-                fill_alive_kernel<<<grid_for(ctx, (M + 31) / 32, 256), 256, 0, st>>>(alive, M);
-                fill_i32_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(placed, M, -1);
+                const bool cl = ctx->world > 1;
+                StagePlan plan = plan_stages(ctx, M, kMaxStagesPerPass, D, true);  // at most one bin per pod
+                int64_t pass_bins = (int64_t)plan.stages * plan.Tn;
+                int *sy = sync_words;
+                uint32_t *al = alive;
+                int32_t *pl = placed;
+                if (cl) {
+                    // cluster mode: the pass's bins are split over the ranks, rank r takes the r-th run of S stages and
+                    // its stage 0 is fed by rank r-1's last stage; all S stages of a rank are resident at once
+                    const int K = nodes_per_thread(D, ctx->rk.nw);
+                    int NS = max_stage_nodes(D, true) / K;
+                    while (NS * K > 32 && (M + (int64_t)NS * K - 1) / ((int64_t)NS * K) < (int64_t)ctx->world * ctx->num_sms) NS >>= 1;
+                    plan.NS = NS;
+                    plan.Tn = NS * K;
+                    const int resident = resident_stages(ctx, D, true, plan.Tn);
+                    if (resident <= 0) return fail(ctx, ACSFIT_E_CUDA, "cluster mode: occupancy query failed");
+                    const int64_t total = std::min<int64_t>((M + plan.Tn - 1) / plan.Tn, (int64_t)ctx->world * resident);
+                    plan.stages = (int)std::max<int64_t>(1, (total + ctx->world - 1) / ctx->world);
+                    if (plan.stages + 8 > kClusterSyncInts) plan.stages = kClusterSyncInts - 8;
+                    pass_bins = (int64_t)ctx->world * plan.stages * plan.Tn;
+                    sy = x_syncset(ctx, ctx->rank, 0);
+                    al = x_alive_of(ctx, ctx->rank);
+                    pl = x_placed_of(ctx, ctx->rank);
+                    if (M > ctx->x_max_pods) return fail(ctx, ACSFIT_E_INVALID, "cluster mode: %lld pods exceed the exchange region", (long long)M);
+                    CUDA_TRY(cudaMemsetAsync(x_status(ctx, ctx->rank), 0, sizeof(int), st));
+                }
+                CUDA_TRY(cudaMemsetAsync(sy, 0, sizeof(int) * (plan.stages + 8), st));
+                if (!cl || ctx->rank == 0) fill_alive_kernel<<<grid_for(ctx, (M + 31) / 32, 256), 256, 0, st>>>(al, M);
+                fill_i32_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(pl, M, -1);
                 ctx->launches += 2;
+                if (cl) TRY(cluster_barrier(ctx, st));  // every rank's counters are zero before anybody polls them
                 PipelineParams pp;
                 memset(&pp, 0, sizeof pp);
                 pp.req = req;
                 pp.pod_idx = list;
                 pp.row_map = row_map;
                 pp.M = M;
-                pp.alive = alive;
-                pp.placed = placed;
+                pp.alive = al;
+                pp.placed = pl;
                 pp.unit = unit_dev + (size_t)t * D;
                 pp.bin_base = bin_base;
-                pp.node_lo = bin_base;
-                pp.node_hi = bin_base + (int64_t)plan.stages * plan.Tn;
+                pp.node_lo = bin_base + (cl ? (int64_t)ctx->rank * plan.stages * plan.Tn : 0);
+                pp.node_hi = pp.node_lo + (int64_t)plan.stages * plan.Tn;
                 pp.Tn = plan.Tn;
                 pp.NS = plan.NS;
                 pp.num_tiles = (int)((M + kTile - 1) / kTile);
-                pp.ticket = ticket;
-                pp.progress = progress;
-                pp.status = status;
-                pp.drained = drained;
+                pp.ticket = sy;
+                pp.progress = sy + 8;
+                pp.status = cl ? x_status(ctx, ctx->rank) : sy + 1;
+                pp.drained = sy + 2;
                 pp.evals = evals_dev;
+                if (cl) {
+                    pp.sys_scope = 1;
+                    if (ctx->rank > 0) {
+                        pp.upstream = x_syncset(ctx, ctx->rank - 1, 0) + 8 + (plan.stages - 1);
+                        pp.alive_in = x_alive_of(ctx, ctx->rank - 1);
+                    }
+                }
                 pp.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+                pp.rk = ctx->rk;
                 if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
                 TRY(launch_pipeline<true>(ctx, D, pp, plan.stages, st));
                 if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+                if (cl) TRY(cluster_merge_placed(ctx, M, placed, st));  // every rank: the pass's complete placements
                 scatter_bins_kernel<<<grid_for(ctx, M, 256), 256, 0, st>>>(list, placed, M, cur_bin, out_bin_of,
                                                                           max_bin_dev);
                 ++ctx->launches;
-                TRY(check_pipeline_status(ctx, status, st));
+                TRY(check_pipeline_status(ctx, pp.status, st));
                 if (ctx->timing) {
                     float ms = 0.f;
                     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1174,8 +1713,9 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
                 ctx->last_tiles += pp.num_tiles;
                 // pods that fitted none of this pass's bins go on to a pass of fresh bins
                 int64_t left = 0;
-                TRY(compact(ctx, BitPred{alive}, M, list, next, block_counts, total_dev, &left, st));
-                bin_base += (int64_t)plan.stages * plan.Tn;
+                if (cl) TRY(compact(ctx, NegPredI32{placed}, M, list, next, block_counts, total_dev, &left, st));
+                else TRY(compact(ctx, BitPred{alive}, M, list, next, block_counts, total_dev, &left, st));
+                bin_base += pass_bins;
                 std::swap(list, next);
                 M = left;
             }
@@ -1206,8 +1746,13 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
         }
     }
     unsigned long long bin_evals = 0;
-    CUDA_TRY(cudaMemcpyAsync(&bin_evals, evals_dev, sizeof bin_evals, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ctx->world > 1) {  // every rank credited the tests of its own bins: sum them (also checks every rank's status)
+        TAKE(sc17, unsigned long long, 17);
+        TRY(cluster_sum_u64(ctx, evals_dev, sc17, &bin_evals, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(&bin_evals, evals_dev, sizeof bin_evals, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     CUDA_TRY(cudaGetLastError());
     evals += bin_evals;
     *out_unaccounted = num_unaccounted;
@@ -1309,10 +1854,11 @@ extern "C" acsfit_status acsfit_first_fit_nodes(acsfit_ctx *ctx, const double *r
     if (!pipeline_dims_ok(D))
         return fail(ctx, ACSFIT_E_INVALID, "first_fit_nodes: D=%d, need 2/4/8/16 (zero columns are neutral)", D);
     reset_stats(ctx);
-    TRY(arena_reserve(ctx, first_fit_scratch(ctx, P, N) + 1024, st));
+    TRY(arena_reserve(ctx, first_fit_scratch(ctx, P, N) + rank_scratch(req_rows, D) + 1024, st));
     ctx->arena_off = 0;
     TAKE(flag, int, 1);
     TRY(check_domain(ctx, req, req_rows * D, flag, st, "req"));
+    if (P > 0 && N > 0) TRY(build_ranks(ctx, req, req_rows, D, st));
     return first_fit_impl(ctx, req, pod_idx, P, D, cap_type, node_type, used_inout, N, out_placed,
                           reinterpret_cast<unsigned long long *>(out_decisions), st);
 }
@@ -1337,10 +1883,11 @@ extern "C" acsfit_status acsfit_fulfill_pending(acsfit_ctx *ctx, const double *r
     if (!pipeline_dims_ok(D))
         return fail(ctx, ACSFIT_E_INVALID, "fulfill_pending: D=%d, need 2/4/8/16 (zero columns are neutral)", D);
     reset_stats(ctx);
-    TRY(arena_reserve(ctx, fulfill_scratch(Pp, T, D) + 1024, st));
+    TRY(arena_reserve(ctx, fulfill_scratch(Pp, T, D) + rank_scratch(Pp, D) + 1024, st));
     ctx->arena_off = 0;
     TAKE(flag, int, 1);
     TRY(check_domain(ctx, req, Pp * D, flag, st, "req"));
+    TRY(build_ranks(ctx, req, Pp, D, st));
     return fulfill_impl(ctx, req, nullptr, Pp, num_listed, D, unit, pool_actual, pool_max, pool_ignored, T,
                         over_provision, out_new_size, out_units_needed, out_bins_opened, out_acc_pool, out_bin_of,
                         out_unaccounted, out_evals, st);
@@ -1422,19 +1969,19 @@ extern "C" acsfit_status acsfit_maintain_actions(acsfit_ctx *ctx, uint8_t *io_st
 // resident stage CTAs the device can hold for the nodes pipeline (all of them must be running before a
 // chained bins pipeline may spin on their progress counters)
 template <int D, bool BINS>
-static int stage_capacity_t(const acsfit_ctx *ctx, int Tn)
+static int stage_capacity_t(acsfit_ctx *ctx, int Tn)
 {
-    constexpr int NT = stage_threads(D, BINS);
-    const size_t smem = std::max(PipelineSmem<D, BINS, NT>::bytes(Tn), (size_t)ctx->smem_floor_kb * 1024);
-    auto kern = firstfit_pipeline_kernel<D, BINS, NT, false>;  // a chained pass fits the GPU, hence runs unpruned
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess) return 0;
-    return per_sm * ctx->num_sms;
+    PipelineParams q;
+    memset(&q, 0, sizeof q);
+    q.Tn = Tn;
+    q.rk = ctx->rk;
+    int resident = 0;  // a chained pass fits the GPU, hence runs unpruned
+    if (launch_pipeline_v<D, BINS, false>(ctx, q, 0, nullptr, &resident) != ACSFIT_OK) return 0;
+    return resident;
 }
 // stage CTAs of BOTH pipelines that can be resident together (conservatively: the smaller of the two
 // per-kernel occupancies, slots taken as interchangeable)
-static int chained_capacity(const acsfit_ctx *ctx, int D, int Tn_nodes, int Tn_bins)
+static int chained_capacity(acsfit_ctx *ctx, int D, int Tn_nodes, int Tn_bins)
 {
     switch (D) {
     case 2: return std::min(stage_capacity_t<2, false>(ctx, Tn_nodes), stage_capacity_t<2, true>(ctx, Tn_bins));
@@ -1498,6 +2045,7 @@ static acsfit_status first_fit_chained(acsfit_ctx *ctx, const double *req, const
     a.drained = sync_n + 2;
     a.progress = sync_n + 8;
     a.watchdog_ns = (unsigned long long)ctx->watchdog_ms * 1000000ull;
+    a.rk = ctx->rk;
 
     PipelineParams b = a;
     b.placed = bins_f;
@@ -1571,7 +2119,7 @@ struct NegPred {
 static size_t scale_up_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N, int T, int D)
 {
     const size_t nblocks = (size_t)((P + kCompactChunk - 1) / kCompactChunk) + 1;
-    return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + sizeof(int32_t) * (size_t)P * 8 +
+    return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + rank_scratch(P, D) + sizeof(int32_t) * (size_t)P * 8 +
            sizeof(int) * (nblocks + kMaxStagesPerPass + 16) + sizeof(double) * (size_t)T * D * 2 + 65536;
 }
 
@@ -1597,6 +2145,7 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
 
     uint64_t decisions = 0;
     TRY(check_domain(ctx, req, P * D, flag, st, "req"));
+    TRY(build_ranks(ctx, req, P, D, st));
     if (T > 0) CUDA_TRY(cudaMemcpyAsync(unit_all_dev, unit_all_host, sizeof(double) * T * D, cudaMemcpyHostToDevice, st));
     // get_pods_to_schedule (cluster.py:217-240)
     CUDA_TRY(cudaMemsetAsync(evals_dev, 0, 2 * sizeof(unsigned long long), st));
@@ -1617,7 +2166,7 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
     if (F > 0) {
         int t0 = 0;
         while (t0 < T && pool_ignored[t0]) ++t0;
-        if (ctx->overlap && ctx->prune != 1 && N > 0 && t0 < T) {  // (forced pruning changes the node kernel: no chaining)
+        if (ctx->overlap && ctx->prune != 1 && N > 0 && t0 < T && ctx->world == 1) {  // (cluster mode: the ranks chain instead)  // (forced pruning changes the node kernel: no chaining)
             TAKE(unit_ord_dev, double, (size_t)T * D);
             TAKE(bins_f, int32_t, F);
             TAKE(j_of_p, int32_t, F);

@@ -35,12 +35,48 @@ namespace acsfit {
 
 constexpr int kTile = 256;         // pods per tile == threads per CTA
 constexpr int kThreads = 256;
-// K: node rows a scanning thread keeps in registers -- K * D = 16 doubles whatever the dimension count
-__host__ __device__ constexpr int nodes_per_thread(int D) { return D <= 4 ? 4 : D <= 8 ? 2 : 1; }
+// K: node rows a scanning thread keeps in registers.  float64 scan (NW == 0): K * D = 16 doubles whatever the
+// dimension count.  Packed-rank scan (NW = 32-bit words per row, see RankLayout): K * NW = 8 words.
+__host__ __device__ constexpr int nodes_per_thread(int D, int NW = 0)
+{
+    return NW == 0 ? (D <= 4 ? 4 : D <= 8 ? 2 : 1) : NW == 1 ? 8 : NW == 2 ? 4 : 2;
+}
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
 constexpr int kMinBatch = 4;  // entries a consumer warp waits for before it starts a batch
 constexpr int kMaxDims = 16;
+
+// Packed-rank form of the scan predicate ("rank compression").  Per resource dimension d the
+// distinct request values of this tick's pod table are sorted; a pod's request is replaced by r' = 1 + its rank,
+// a node's (bin's) scan threshold by t' = #{distinct values <= thr}.  Because every request value is IN the
+// table,  req_d <= thr_d  <=>  r'_d <= t'_d  exactly.  All D fields of a row are packed into NW 32-bit words,
+// each field followed by one guard bit; then
+//        fits in every dimension  <=>  (((T | G) - R) & G) == G          (G = the guard bits)
+// one integer subtract and one three-input logic op per word instead of D float64 compares per pair.  No field
+// borrows from its neighbour: a field of (T | G) - R is 2^bits + t' - r' >= 1.  The resolver keeps evaluating
+// the literal float64 reference expression; only the candidate scan uses ranks.
+constexpr int kRankCap = 8192;     // distinct values per dimension the table can hold (else: float64 scan)
+constexpr int kRankSlots = 32768;  // hash slots per dimension while the table is built
+struct RankLayout {
+    int nw;                        // words per row: 0 (not available), 1, 2 or 4
+    uint32_t guard[4];             // G
+    uint8_t word[16];              // word that holds dimension d
+    uint8_t shift[16];             // bit position of its field
+    int32_t count[16];             // U_d = number of distinct values
+    const double *sorted;          // [D][kRankCap] ascending distinct values (device)
+    const uint32_t *packed;        // [req rows][nw] packed pod ranks (device)
+};
+
+// t' = number of table values <= thr   (thr = -1: none fits -> 0; thr = +inf -> U)
+__device__ __forceinline__ uint32_t rank_upper(const double *__restrict__ sorted_d, int U, double thr)
+{
+    int lo = 0, hi = U;  // invariant: sorted[< lo] <= thr, sorted[>= hi] > thr
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(sorted_d + mid) <= thr) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
 
 struct PipelineParams {
     // pod side
@@ -69,7 +105,14 @@ struct PipelineParams {
     int *status;            // 1 int, zeroed: != 0 -> abort (watchdog)
     int *drained;           // 1 int, zeroed: set by the first stage that forwards no pod at all
     const int *upstream;    // optional: progress counter of ANOTHER pipeline's last stage that feeds stage 0
-                            // of this one (bins pipeline chained behind the nodes pipeline), or nullptr
+                            // of this one (bins pipeline chained behind the nodes pipeline; or the previous
+                            // rank's pipeline in cluster mode, then a peer-memory pointer), or nullptr
+    const uint32_t *alive_in; // optional: stage 0 reads the tile's alive words HERE (the upstream pipeline's
+                            // bitmap in a peer GPU's memory) and always writes them to `alive`
+    int sys_scope;          // cluster mode: upstream poll and the last stage's publish use system scope
+    int tile_lo;            // first tile of this launch in the pod list (pod blocks); tiles are numbered
+                            // locally in the progress counters, globally in alive / placed / pod_idx
+    RankLayout rk;          // packed-rank scan tables (rk.nw == NW of the instantiation)
     unsigned long long *evals; // bins mode: credited bin tests (atomicAdd)
     unsigned long long watchdog_ns;
     unsigned long long *prof;  // optional [stages][8] clock64 phase totals (developer probe), or nullptr
@@ -86,6 +129,23 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// system scope: the counter / flag is polled by a kernel running on ANOTHER GPU (NVLink peer memory)
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -109,7 +169,7 @@ __device__ __forceinline__ void load_row(double (&r)[D], const double *src)
 // dynamic shared memory layout (doubles first for alignment).
 // nodes mode keeps three [D][Tn] arrays: scan thresholds, used (the mutable state) and capacity;
 // bins mode keeps one: the remaining capacity IS the threshold (finite values, Lemma B).
-template <int D, bool BINS, int NT, bool PRUNE = false>
+template <int D, bool BINS, int NT, bool PRUNE = false, int RW = 0>
 struct PipelineSmem {
     static constexpr int NW = NT / 32;  // warps per stage CTA == resolver warps
     static __host__ __device__ size_t bytes(int Tn)
@@ -118,7 +178,8 @@ struct PipelineSmem {
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
                                      NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
-               + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/;
+               + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/
+               + sizeof(unsigned) * ((size_t)RW * Tn /*packed node words*/ + (size_t)RW * kTile /*packed pod words*/ + 4 /*alignment*/);
     }
 };
 
@@ -148,11 +209,11 @@ __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, in
     return e;
 }
 
-template <int D, bool BINS, int NT, bool PRUNE>
+template <int D, bool BINS, int NT, bool PRUNE, int RW>
 __global__ void __launch_bounds__(NT)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
-    constexpr int K = nodes_per_thread(D);
+    constexpr int K = nodes_per_thread(D, RW);  // RW: 32-bit words of a packed-rank row, 0 = float64 scan
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Tn = p.Tn;
@@ -175,6 +236,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
     unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
     unsigned char *found_s = reinterpret_cast<unsigned char *>(slot_of + kTile);  // [NW][32] node that took dense entry k
+    // packed-rank rows (RW > 0): scan thresholds of the stage's nodes and the compacted pods of the tile
+    unsigned *tw_s = reinterpret_cast<unsigned *>((reinterpret_cast<uintptr_t>(found_s + NW * 32) + 15) & ~(uintptr_t)15);  // [Tn][RW]
+    unsigned *rw_s = tw_s + (size_t)RW * Tn;                                                                              // [kTile][RW]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -189,6 +253,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
     }
     __syncthreads();
     const int stage = (int)misc[0];
+    const bool remote_in = stage == 0 && p.alive_in != nullptr;            // this stage is fed by another GPU
+    const bool sys_out = p.sys_scope && stage == (int)gridDim.x - 1;       // ... and this one feeds another GPU
+    auto publish = [&](int tiles_done) {
+        if (sys_out) {
+            __threadfence_system();
+            st_release_sys(p.progress + stage, tiles_done);
+        } else {
+            st_release(p.progress + stage, tiles_done);
+        }
+    };
     const int64_t stage_lo = p.node_lo + (int64_t)stage * Tn;   // global index of local node 0
     const int n_valid = (int)max((int64_t)0, min((int64_t)Tn, p.node_hi - stage_lo));
     const int n_warps = (n_valid + 31) >> 5;                     // resolver warps that own a real node
@@ -217,7 +291,20 @@ firstfit_pipeline_kernel(const PipelineParams p)
         dirty[tid] = 0;
     }
     for (int i = tid; i < NW * (kTile + 1) + 1; i += NT) hitlist[i] = 0;  // hit list + the NW-1 queues
+    if constexpr (RW > 0)
+        for (int i = tid; i < Tn * RW; i += NT) tw_s[i] = 0;
     __syncthreads();
+    // (n, d) -> field t' of the node's packed threshold row; callers zero the row first
+    auto pack_field = [&](int i) {
+        const int d = i / Tn, n = i - d * Tn;
+        const double thr = BINS ? state_s[i] : thr_s[i];
+        const uint32_t t = rank_upper(p.rk.sorted + (size_t)d * kRankCap, p.rk.count[d], thr);
+        atomicOr(&tw_s[n * RW + p.rk.word[d]], t << p.rk.shift[d]);
+    };
+    if constexpr (RW > 0) {
+        for (int i = tid; i < Tn * D; i += NT) pack_field(i);
+        // made visible by the barrier inside / after refresh_bounds or by (S1) of the first tile
+    }
 
     // Per-warp, per-dimension upper bound of the request that can still fit SOME node of the warp (nodes: the
     // scan thresholds, bins: the remaining amounts).  Kept in shared memory, refreshed after every tile that
@@ -266,8 +353,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
     // the pod list is static, so the row of this thread's entry in the NEXT tile can be fetched from L2
     // while the current tile is scanned; only the alive word has to wait for the upstream stage.
     double pre[D];
+    unsigned prew[RW > 0 ? RW : 1];
     auto prefetch_row = [&](int tile) {
-        const int64_t j = (int64_t)tile * kTile + tid;
+        const int64_t j = (int64_t)(p.tile_lo + tile) * kTile + tid;
         if (tid < kTile && tile < p.num_tiles && j < p.M) {
             int64_t row = p.pod_idx ? (int64_t)__ldg(p.pod_idx + j) : j;
             if (p.row_map) row = (int64_t)__ldg(p.row_map + row);
@@ -277,6 +365,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 const double2 v = __ldg(reinterpret_cast<const double2 *>(src + d));
                 pre[d] = v.x;
                 pre[d + 1] = v.y;
+            }
+            if constexpr (RW > 0) {
+#pragma unroll
+                for (int w = 0; w < RW; ++w) prew[w] = __ldg(p.rk.packed + (size_t)row * RW + w);
             }
         }
     };
@@ -294,7 +386,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     // an earlier stage finished with nothing left alive: every remaining tile is empty
                     misc[2] = 1;
                 } else
-                while (ld_acquire(flag) <= tile) {
+                while ((p.sys_scope && stage == 0 ? ld_acquire_sys(flag) : ld_acquire(flag)) <= tile) {
                     if ((++spins & 63u) == 0) {
                         if (*(volatile int *)p.status != 0 ||
                             global_timer_ns() - t_start > p.watchdog_ns) {
@@ -313,8 +405,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
         ACSFIT_PROF(0)
 
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
-        const int64_t j = (int64_t)tile * kTile + tid;
-        const unsigned word = (tid < kTile && j < p.M) ? __ldcg(p.alive + (j >> 5)) : 0u;
+        const int64_t j = (int64_t)(p.tile_lo + tile) * kTile + tid;
+        const unsigned word = (tid < kTile && j < p.M) ? (remote_in ? ld_relaxed_sys_u32(p.alive_in + (j >> 5)) : __ldcg(p.alive + (j >> 5))) : 0u;
         const bool is_alive = (word >> lane) & 1u;
         bool pass = is_alive;
         if (PRUNE && is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
@@ -342,7 +434,13 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (!PRUNE) alive_total = total;
         if (total == 0) {  // nothing alive, or nothing that could fit here: forward the tile untouched
             if (PRUNE) forwarded += (long long)alive_total;
-            if (tid == 0) st_release(p.progress + stage, tile + 1);
+            if (remote_in && warp == 0) {  // the words came from the upstream GPU: this GPU's bitmap must hold them too
+                const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + lane;
+                if (lane < kTile / 32 && wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
+                __syncwarp();
+                if (lane == 0) __threadfence();
+            }
+            if (tid == 0) publish(tile + 1);
             prefetch_row(tile + 1);
             continue;  // uniform: every thread sees the same total; (S1) protects the shared words
         }
@@ -353,6 +451,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
             for (int d = 0; d < D; d += 2) *reinterpret_cast<double2 *>(dst + d) = make_double2(pre[d], pre[d + 1]);
             slot_of[pos] = (unsigned short)tid;
             cand[pos] = kNoCand;
+            if constexpr (RW > 0) {
+#pragma unroll
+                for (int w = 0; w < RW; ++w) rw_s[pos * RW + w] = prew[w];
+            }
         }
         prefetch_row(tile + 1);
         __syncthreads();
@@ -370,6 +472,58 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         if (all_hit) {
             if (tid < total) cand[tid] = 0;
+        } else if constexpr (RW > 0) {
+            // packed-rank scan: fits in every dimension <=> (((T | G) - R) & G) == G, word by word (RankLayout)
+            unsigned g[RW], tg[K][RW];
+#pragma unroll
+            for (int w = 0; w < RW; ++w) g[w] = p.rk.guard[w];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int w = 0; w < RW; ++w) tg[k][w] = tw_s[(slot + k * NS) * RW + w] | g[w];
+            constexpr int PPI = 4;  // pods per thread and iteration
+            for (unsigned qb = 0; qb < total; qb += PPI * PG) {
+                unsigned q[PPI], best[PPI], r[PPI][RW];
+                bool live[PPI];
+#pragma unroll
+                for (int i = 0; i < PPI; ++i) {
+                    q[i] = qb + (unsigned)(i * PG + group);
+                    live[i] = q[i] < total;
+                    const unsigned *src = rw_s + (size_t)(live[i] ? q[i] : total - 1) * RW;
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) r[i][w] = src[w];
+                    best[i] = kNoCand;
+                }
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+#pragma unroll
+                    for (int i = 0; i < PPI; ++i) {
+                        unsigned miss = 0;
+#pragma unroll
+                        for (int w = 0; w < RW; ++w) miss |= ((tg[k][w] - r[i][w]) & g[w]) ^ g[w];
+                        if (miss == 0 && live[i]) best[i] = (unsigned)(slot + k * NS);
+                    }
+                }
+                unsigned any_best = best[0];
+#pragma unroll
+                for (int i = 1; i < PPI; ++i) any_best &= best[i];
+                if (__any_sync(0xFFFFFFFFu, any_best != kNoCand)) {
+                    const int seg = NS < 32 ? NS : 32;
+                    for (int o = seg >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < PPI; ++i) best[i] = min(best[i], __shfl_xor_sync(0xFFFFFFFFu, best[i], o));
+                    }
+                    if ((lane & (seg - 1)) == 0) {
+#pragma unroll
+                        for (int i = 0; i < PPI; ++i) {
+                            if (best[i] != kNoCand) {
+                                if (NS <= 32) cand[q[i]] = best[i];
+                                else atomicMin(&cand[q[i]], best[i]);
+                            }
+                        }
+                    }
+                }
+            }
         } else {
             double t[K][D];
 #pragma unroll
@@ -481,6 +635,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                                  : PRUNE ? wmax[warp * D + d] : warp_upper_bound(n < Tn ? thr_s[(size_t)d * Tn + n] : -1.0);
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
+                unsigned touched_tile = 0u;  // nodes / bins of this warp that took a pod in this tile
                 unsigned ev_local = 0;
                 const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
@@ -610,6 +765,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         ev_local += __reduce_add_sync(0xFFFFFFFFu, got ? (unsigned)found + 1u : 0u) -
                                     (unsigned)__popc(acc_lanes & ~touched_or_open);
                         touched_or_open |= acc_lanes;
+                        touched_tile |= acc_lanes;
                     }
                     if (BINS && took) {  // tighten the bound: the remaining amounts just shrank
 #pragma unroll
@@ -623,7 +779,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     }
                     if (tracing) t_loop += clock64() - t_l0;
                     if (placed_here >= 0) {  // bookkeeping off the critical path, one lane per placed entry
-                        p.placed[(int64_t)tile * kTile + s_l] = (int32_t)(stage_lo + my_lo + placed_here);
+                        p.placed[(int64_t)(p.tile_lo + tile) * kTile + s_l] = (int32_t)(stage_lo + my_lo + placed_here);
                         atomicAnd(&alive_w[s_l >> 5], ~(1u << (s_l & 31)));
                     }
                     head += (unsigned)n_ent;
@@ -644,7 +800,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     }
                     if (lane == 0) {
                         if (BINS) opened[warp] = touched_or_open;
-                        else dirty[warp] = touched_or_open;
+                        dirty[warp] = touched_tile;
                     }
                 }
             }
@@ -660,11 +816,20 @@ firstfit_pipeline_kernel(const PipelineParams p)
         const unsigned n_placed_tile = nh ? misc[4] : 0u;
 
         // ---- nodes: refresh the scan thresholds of the nodes that took a pod (all threads) ----
-        if (!BINS && n_placed_tile) {
+        if ((!BINS || RW > 0) && n_placed_tile) {
+            if constexpr (RW > 0) {  // the packed rows of the nodes that took a pod are rebuilt field by field
+                for (int i = tid; i < Tn * RW; i += NT) {
+                    const int n = i / RW;
+                    if ((dirty[n >> 5] >> (n & 31)) & 1u) tw_s[i] = 0;
+                }
+                __syncthreads();
+            }
             for (int i = tid; i < Tn * D; i += NT) {
                 const int d = i / Tn, n = i - d * Tn;
-                if ((dirty[n >> 5] >> (n & 31)) & 1u)
-                    thr_s[i] = node_threshold(cap_s[i], state_s[i]);
+                if ((dirty[n >> 5] >> (n & 31)) & 1u) {
+                    if (!BINS) thr_s[i] = node_threshold(cap_s[i], state_s[i]);
+                    if constexpr (RW > 0) pack_field(i);
+                }
             }
         }
         // node state changed: new bounds for the next tile (visible after its (S1))
@@ -677,14 +842,14 @@ firstfit_pipeline_kernel(const PipelineParams p)
         // ---- publish the surviving pods of the tile (warp 0; the others go on to the next tile) ----
         if (warp == 0) {
             forwarded += (long long)alive_total - (long long)n_placed_tile;
-            if (lane < kTile / 32 && n_placed_tile) {
-                const int64_t wj = (int64_t)tile * (kTile / 32) + lane;
+            if (lane < kTile / 32 && (n_placed_tile || remote_in)) {
+                const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + lane;
                 if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
             }
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
-                st_release(p.progress + stage, tile + 1);
+                publish(tile + 1);
             }
         }
         ACSFIT_PROF(4)
@@ -708,7 +873,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     }
     if (BINS && lane == 0 && my_evals) atomicAdd(p.evals, my_evals);  // every warp credits its own placements
     if (tid == 0) {
-        if (misc[2]) st_release(p.progress + stage, p.num_tiles);
+        if (misc[2]) publish(p.num_tiles);
         if (forwarded == 0) atomicExch(p.drained, 1);
         if (p.prof) {
             for (int i = 0; i < 8; ++i) p.prof[(size_t)stage * 8 + i] = prof_acc[i];

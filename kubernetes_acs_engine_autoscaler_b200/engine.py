@@ -87,8 +87,42 @@ class Engine(object):
     def set_timing(self, enabled):
         self._check(self._lib.acsfit_ctx_set_timing(self._ctx, 1 if enabled else 0))
 
+    def set_knob(self, name, value):
+        """developer knobs of include/acsfit.h ("ranks", "prune", "overlap", "min_stages", "cluster_blocks")."""
+        self._check(self._lib.acsfit_ctx_set_knob(self._ctx, name.encode(), int(value)))
+
     def configure(self, min_stages=0, watchdog_ms=0):
         self._check(self._lib.acsfit_ctx_configure(self._ctx, int(min_stages), int(watchdog_ms)))
+
+    # ------------------------------------------------------------------ cluster mode (one cluster, all GPUs of a box)
+    def cluster_connect(self, max_pods, max_nodes, max_dims=16):
+        """join the ranks of the default torch.distributed group into ONE cluster (include/acsfit.h, "Cluster
+        mode"): every rank exports its exchange region (CUDA IPC), the handles are all-gathered here and opened
+        by the library.  Afterwards first_fit_nodes / fulfill_pending / scale_up / scale_up_host must be called by
+        all ranks with identical (replicated) inputs; each returns the complete result."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        handle = (ctypes.c_ubyte * 64)()
+        self._check(self._lib.acsfit_cluster_init(self._ctx, rank, world, int(max_pods), int(max_nodes),
+                                                  int(max_dims), ctypes.cast(handle, ctypes.c_void_p)))
+        where = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=where)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        self._check(self._lib.acsfit_cluster_connect(self._ctx, ctypes.cast(buf, ctypes.c_void_p)))
+        dist.barrier()  # every rank has zeroed and mapped every region before the first in-stream barrier
+        self.cluster_world = world
+        return world
+
+    def cluster_barrier(self):
+        self._check(self._lib.acsfit_cluster_barrier(self._ctx, self._stream()))
+
+    def cluster_last_plan(self):
+        v = [ctypes.c_int() for _ in range(4)]
+        self._check(self._lib.acsfit_cluster_last_plan(self._ctx, *[ctypes.cast(ctypes.byref(x), ctypes.c_void_p) for x in v]))
+        return {"stage_nodes": v[0].value, "stages": v[1].value, "pod_blocks": v[2].value, "resident": v[3].value}
 
     @property
     def launch_count(self):

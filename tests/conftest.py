@@ -21,9 +21,10 @@ def oracle_mod():
     return oracle
 
 
-@pytest.fixture(scope="session")
-def engine():
-    """the product engine on cuda:0; GPU tests only."""
+@pytest.fixture(scope="session", params=["ranks", "f64"])
+def engine(request):
+    """the product engine on cuda:0; GPU tests only.  Every test runs with both forms of the candidate scan:
+    packed-rank integer compares (the default) and float64 compares (the fallback for huge request tables)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -31,5 +32,6 @@ def engine():
     acs_build.build()
     from kubernetes_acs_engine_autoscaler_b200.engine import Engine
     eng = Engine(0, watchdog_ms=15000)
+    eng.set_knob("ranks", 1 if request.param == "ranks" else 0)
     yield eng
     eng.close()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     lib.acsfit_abi_version.restype = ctypes.c_int
-    assert lib.acsfit_abi_version() == 1
+    assert lib.acsfit_abi_version() == 2  # 2: cluster-mode entry points
     # the python binding table covers the header too
     from kubernetes_acs_engine_autoscaler_b200 import _native
     assert set(names) <= set(_native.SIGNATURES)
