@@ -18,7 +18,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ACSFIT_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """the reference where it lies in the build container, else the copy oracle/build_ref.py staged in the
+    git-ignored oracle/_ref/ (which travels to the GPU box with the snapshot)."""
+    if os.path.isdir("/root/reference/autoscaler"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("ACSFIT_REFERENCE_ROOT", _default_root())
 
 
 def available():
