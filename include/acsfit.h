@@ -253,6 +253,11 @@ ACSFIT_API acsfit_status acsfit_scale_up_host(acsfit_ctx *ctx, const double *req
                                    int64_t *out_units_needed, int64_t *out_bins_opened,
                                    int32_t *out_acc_pool, uint64_t *out_counters);
 
+/* acsfit_occupancy_host = acsfit_occupancy with host buffers (reference cluster.py:165-168): R rows of req_run,
+ * used_inout N x D is read, updated and written back. */
+ACSFIT_API acsfit_status acsfit_occupancy_host(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                    const double *req_run, int64_t R, int64_t N, int D, double *used_inout);
+
 /* acsfit_maintain_host = node_states (one threshold) + maintain_actions with host buffers
  * (reference engine_scaler.py:120-182, scaler.py:61-114). out_state/out_action N bytes. */
 ACSFIT_API acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,

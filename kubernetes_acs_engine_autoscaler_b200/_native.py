@@ -33,6 +33,7 @@ SIGNATURES = {
                                 c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acsfit_scale_up_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64,
                                      c_vp, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "acsfit_occupancy_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
     "acsfit_maintain_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
                                      c_i64, c_int, c_int, c_i64, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "acsfit_cluster_init": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_int, c_vp]),

@@ -4,9 +4,9 @@ The hot path ends where the reference hands `new_pool_sizes` to `scale_pools` an
 actions to kube.py's mutators.  Everything below that line (Azure login, ARM template
 download / unrolling, deployments, VM deletion: reference autoscaler/azure_api.py,
 template_processing.py) is cloud I/O that a deployment keeps from the reference package.
-This module resolves those functions lazily from the reference's own modules when they are
-importable (`autoscaler.azure_api`, `autoscaler.template_processing`) or from a module named
-by $ACSFIT_ADAPTER_MODULE, and raises a clear error otherwise.  With --dry-run none of them
+This module resolves those functions lazily from a module named by $ACSFIT_ADAPTER_MODULE, from this package's
+own template_processing.py (the ARM template unrolling), or from the reference's modules when
+they are importable (`autoscaler.azure_api`), and raises a clear error otherwise.  With --dry-run none of them
 is ever called (engine_scaler.py:79-88, :154-178).
 """
 import importlib
@@ -33,6 +33,8 @@ def resolve(name):
     candidates = []
     if os.environ.get("ACSFIT_ADAPTER_MODULE"):
         candidates.append(os.environ["ACSFIT_ADAPTER_MODULE"])
+    if _NAMES[name] == "template_processing":  # the template unrolling is part of this package now
+        candidates.append(__package__ + ".template_processing")
     candidates.append("autoscaler." + _NAMES[name])
     for mod in candidates:
         try:

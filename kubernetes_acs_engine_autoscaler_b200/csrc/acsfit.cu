@@ -2358,6 +2358,32 @@ extern "C" acsfit_status acsfit_scale_up_host(acsfit_ctx *ctx, const double *req
     return ACSFIT_OK;
 }
 
+extern "C" acsfit_status acsfit_occupancy_host(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
+                                               const double *req_run, int64_t R, int64_t N, int D, double *used_inout)
+{
+    TRY(enter(ctx, D));
+    cudaStream_t st = nullptr;
+    if (N < 0 || R < 0 || (N > 0 && (!row_ptr || !used_inout)) || (R > 0 && !req_run))
+        return fail(ctx, ACSFIT_E_INVALID, "occupancy_host: bad arguments");
+    if (N == 0) return ACSFIT_OK;
+    const int64_t nnz = row_ptr[N];
+    if (nnz < 0 || (nnz > 0 && !run_idx)) return fail(ctx, ACSFIT_E_INVALID, "occupancy_host: bad CSR");
+    TRY(hbuf_reserve(ctx, sizeof(int64_t) * ((size_t)N + 1) + sizeof(int32_t) * (size_t)nnz +
+                              sizeof(double) * ((size_t)R * D + (size_t)N * D) + 8 * 256));
+    HTAKE(d_ptr, int64_t, (size_t)N + 1);
+    HTAKE(d_req, double, (size_t)R * D);
+    HTAKE(d_used, double, (size_t)N * D);
+    HTAKE(d_idx, int32_t, nnz);
+    H2D(d_ptr, row_ptr, sizeof(int64_t) * ((size_t)N + 1));
+    H2D(d_req, req_run, sizeof(double) * (size_t)R * D);
+    H2D(d_used, used_inout, sizeof(double) * (size_t)N * D);
+    H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
+    TRY(acsfit_occupancy(ctx, d_ptr, d_idx, d_req, N, D, d_used, st));
+    D2H(used_inout, d_used, sizeof(double) * (size_t)N * D);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ACSFIT_OK;
+}
+
 extern "C" acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
                                               const double *req_run, const uint8_t *flags_run, int64_t R,
                                               const double *cap_type, int K, const int32_t *node_type,

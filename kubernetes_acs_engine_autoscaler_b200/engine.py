@@ -296,6 +296,15 @@ class Engine(object):
                     "num_unaccounted": int(counters[2]), "decisions": int(counters[3])})
         return res
 
+    def occupancy_host(self, row_ptr, run_idx, req_run, used):
+        """cluster.py:165-168 with HOST arrays; `used` [N, D] float64 is updated in place."""
+        assert isinstance(used, np.ndarray) and used.dtype == np.float64 and used.flags.c_contiguous
+        N, D = used.shape
+        req_run = _np(req_run, np.float64).reshape(-1, D)
+        self._check(self._lib.acsfit_occupancy_host(self._ctx, _ptr(_np(row_ptr, np.int64)), _ptr(_np(run_idx, np.int32)),
+                                                    _ptr(req_run), req_run.shape[0], N, D, _ptr(used)))
+        return used
+
     def maintain_host(self, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age,
                       node_pool, any_pending, idle_threshold, budget0, pool_scalable, dry_run):
         cap_type = _np(cap_type, np.float64)
