@@ -42,6 +42,8 @@ struct acsfit_ctx {
     int x_max_dims = 0;
     int epoch = 0;                                      // in-stream barrier count (same on every rank)
     int force_blocks = 0;                               // developer knob "cluster_blocks"
+    int inject_chain_timeout = 0;                       // test knob: treat the next n chained launches as timed out
+    int chain_fallbacks = 0;                            // chained nodes+bins launches that hit the watchdog and were redone unchained
     int cl_tn = 0, cl_stages = 0, cl_blocks = 0, cl_resident = 0;  // geometry of the last cluster node pass
     int smem_floor_kb = 0;    // >0: request at least this much dynamic smem per stage CTA (limits CTAs per SM)
     char err[512] = {0};
@@ -785,6 +787,7 @@ extern "C" acsfit_status acsfit_ctx_set_knob(acsfit_ctx *ctx, const char *name, 
     else if (!strcmp(name, "overlap")) ctx->overlap = value != 0;
     else if (!strcmp(name, "min_stages")) ctx->min_stages = std::max(0, value);
     else if (!strcmp(name, "cluster_blocks")) ctx->force_blocks = std::max(0, value);
+    else if (!strcmp(name, "inject_chain_timeout")) ctx->inject_chain_timeout = std::max(0, value);
     else return fail(ctx, ACSFIT_E_INVALID, "unknown knob %s", name);
     return ACSFIT_OK;
 }
@@ -2120,6 +2123,7 @@ static size_t scale_up_scratch(const acsfit_ctx *ctx, int64_t P, int64_t N, int 
 {
     const size_t nblocks = (size_t)((P + kCompactChunk - 1) / kCompactChunk) + 1;
     return first_fit_scratch(ctx, P, N) + fulfill_scratch(P, T, D) + rank_scratch(P, D) + sizeof(int32_t) * (size_t)P * 8 +
+           sizeof(double) * (size_t)(N + 1) * D /*used backup of the chained launch*/ +
            sizeof(int) * (nblocks + kMaxStagesPerPass + 16) + sizeof(double) * (size_t)T * D * 2 + 65536;
 }
 
@@ -2183,8 +2187,27 @@ static acsfit_status scale_up_impl(acsfit_ctx *ctx, const double *req, int64_t P
             if (inel == 0) {
                 int64_t covered = 0;
                 uint64_t bev = 0;
-                TRY(first_fit_chained(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1,
-                                      unit_ord_dev + (size_t)t0 * D, bins_f, &covered, &bev, &chained, st));
+                // The chained launch needs every stage CTA of both grids resident at once; the occupancy query cannot see
+                // SMs another context holds (a shared GPU, MPS).  If the watchdog fires, the node state is restored from
+                // this copy and the tick is redone unchained (and the ctx stops chaining) instead of failing.
+                TAKE(used_backup, double, (size_t)N * D);
+                CUDA_TRY(cudaMemcpyAsync(used_backup, used, sizeof(double) * (size_t)N * D, cudaMemcpyDeviceToDevice, st));
+                acsfit_status cs = first_fit_chained(ctx, req, list_f, F, D, cap_type, node_type, used, N, placed_f, evals_dev + 1,
+                                                     unit_ord_dev + (size_t)t0 * D, bins_f, &covered, &bev, &chained, st);
+                if (cs == ACSFIT_OK && chained && ctx->inject_chain_timeout > 0) {  // test hook: exercise the recovery path
+                    --ctx->inject_chain_timeout;
+                    cs = ACSFIT_E_TIMEOUT;
+                }
+                if (cs == ACSFIT_E_TIMEOUT) {
+                    CUDA_TRY(cudaStreamSynchronize(ctx->side));
+                    CUDA_TRY(cudaMemcpyAsync(used, used_backup, sizeof(double) * (size_t)N * D, cudaMemcpyDeviceToDevice, st));
+                    ctx->overlap = false;
+                    ++ctx->chain_fallbacks;
+                    chained = false;
+                    reset_stats(ctx);
+                } else if (cs != ACSFIT_OK) {
+                    return cs;
+                }
                 if (chained) {
                     // pending pods in list order: their feasible positions, pod numbers and first-pass bins
                     TRY(compact(ctx, NegPred{placed_f}, F, nullptr, j_of_p, block_counts, total_dev, &Pn, st));

@@ -300,3 +300,28 @@ def test_streaming_kernels_ragged_and_permuted(engine, oracle_mod, N, D, seed):
                                 engine.dev(cap_type, torch.float64), engine.dev(node_type, torch.int32),
                                 engine.dev(node_flags, torch.uint8), engine.dev(node_age, torch.int64), any_pending, thr)
         np.testing.assert_array_equal(to_np(st), st_o)
+
+
+def test_chained_launch_timeout_falls_back_unchained(engine, oracle_mod):
+    """a watchdog abort of the chained nodes+bins launch (possible when another context holds SMs) must not fail
+    the tick: the node state is restored and the tick redone unchained, with the same result"""
+    c = syn.make_cluster(20000, 2000, 4, 1, seed=31)
+    used0 = syn.initial_used(c)
+    args = (c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"], c["pool_ignored"], c["over_provision"])
+    f64, i32 = torch.float64, torch.int32
+
+    def tick():
+        used = engine.dev(used0, f64)
+        r = engine.scale_up(engine.dev(c["req"], f64), *args, engine.dev(c["cap_type"], f64), engine.dev(c["node_type"], i32), used)
+        return r, to_np(used)
+    try:
+        r_ok, used_ok = tick()
+        engine.set_knob("inject_chain_timeout", 1)
+        r_fb, used_fb = tick()          # first attempt "times out", second runs unchained
+    finally:
+        engine.set_knob("inject_chain_timeout", 0)
+        engine.set_knob("overlap", 1)   # the fallback switches chaining off for the ctx: restore for later tests
+    np.testing.assert_array_equal(to_np(r_ok["placed"]), to_np(r_fb["placed"]))
+    np.testing.assert_array_equal(bits(used_ok), bits(used_fb))
+    np.testing.assert_array_equal(r_ok["new_size"], r_fb["new_size"])
+    assert r_ok["decisions"] == r_fb["decisions"] and r_ok["n_pending"] == r_fb["n_pending"] > 0
