@@ -176,7 +176,7 @@ struct PipelineSmem {
     {
         return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/ + (PRUNE ? (size_t)(NW + 1) * D : 0) /*warp bounds + stage bound*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
-                                     NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + (kTile + 1) /*hitlist*/ +
+                                     NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + 8 /*next alive words*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
                + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/
                + sizeof(unsigned) * ((size_t)RW * Tn /*packed node words*/ + (size_t)RW * kTile /*packed pod words*/ + 4 /*alignment*/);
@@ -232,7 +232,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
     unsigned *wcount = dirty + NW;                              // [8] pods to scan per tile word
     unsigned *acount = wcount + 8;                              // [8] alive pods per tile word
     unsigned *misc = acount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
-    unsigned *hitlist = misc + 8;                               // [kTile+1] ordered hit entries (q+1), then kQueueEnd
+    unsigned *nextw = misc + 8;                                 // [8] alive words of the tile about to be loaded
+    unsigned *hitlist = nextw + 8;                              // [kTile+1] ordered hit entries (q+1), then kQueueEnd
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
     unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
     unsigned char *found_s = reinterpret_cast<unsigned char *>(slot_of + kTile);  // [NW][32] node that took dense entry k
@@ -378,8 +379,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (p.prof && tid == 0) tp = clock64();
         // ---- wait until the previous stage has published this tile (warp 1 polls, so that warp 0
         //      can still be publishing the previous tile) ---------------------------------------
-        if (stage > 0 || p.upstream) {
-            if (tid == 32) {
+        //      The same warp then fetches the tile's alive words, so that their L2 (or NVLink) latency is
+        //      paid while the other warps are still finishing the previous tile, not after the barrier.
+        if (warp == 1) {
+            if ((stage > 0 || p.upstream) && lane == 0) {
                 const int *flag = stage > 0 ? p.progress + (stage - 1) : p.upstream;
                 unsigned spins = 0;
                 if (stage > 0 && *(volatile int *)p.drained) {
@@ -398,15 +401,22 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     __nanosleep(20);
                 }
             }
+            __syncwarp();  // the acquire above orders the loads below (all lanes of this warp)
+            if (lane < kTile / 32) {
+                const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + lane;
+                unsigned w = 0u;
+                if (wj * 32 < p.M) w = remote_in ? ld_relaxed_sys_u32(p.alive_in + wj) : __ldcg(p.alive + wj);
+                nextw[lane] = w;
+            }
         }
-        __syncthreads();  // (S1) previous tile fully retired (publish included), poll result visible
+        __syncthreads();  // (S1) previous tile fully retired (publish included), poll result and alive words visible
         if (misc[1]) return;  // watchdog: give up (host reports ACSFIT_E_TIMEOUT)
         if (misc[2]) break;   // drained: nothing left to do (state write-back below)
         ACSFIT_PROF(0)
 
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
         const int64_t j = (int64_t)(p.tile_lo + tile) * kTile + tid;
-        const unsigned word = (tid < kTile && j < p.M) ? (remote_in ? ld_relaxed_sys_u32(p.alive_in + (j >> 5)) : __ldcg(p.alive + (j >> 5))) : 0u;
+        const unsigned word = nextw[warp];
         const bool is_alive = (word >> lane) & 1u;
         bool pass = is_alive;
         if (PRUNE && is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
@@ -636,6 +646,15 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned touched_tile = 0u;  // nodes / bins of this warp that took a pod in this tile
+                // this lane's node as a packed-rank row (scan thresholds at tile start: what fits it NOW is a subset)
+                unsigned rk_g[RW > 0 ? RW : 1], rk_t[RW > 0 ? RW : 1];
+                if constexpr (RW > 0) {
+#pragma unroll
+                    for (int w = 0; w < RW; ++w) {
+                        rk_g[w] = p.rk.guard[w];
+                        rk_t[w] = (n < Tn ? tw_s[n * RW + w] : 0u) | rk_g[w];
+                    }
+                }
                 unsigned ev_local = 0;
                 const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
@@ -693,6 +712,21 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     bool poss = (testmask >> lane) & 1u;
 #pragma unroll
                     for (int d = 0; d < D; ++d) poss = poss & (own[d] <= Mx[d]);
+                    if constexpr (RW > 0) {
+                        // exact (at tile start) pair test of every entry of the batch against every node of the warp in
+                        // rank space: three integer ops per pair and word.  An entry no node could take at tile start
+                        // can be taken by none now (nodes only fill up): it skips the sequential float64 loop.
+                        unsigned fitbits = 0u;
+                        for (int i = 0; i < n_ent; ++i) {  // warp-uniform trip count
+                            const unsigned qi = __shfl_sync(0xFFFFFFFFu, q_l, i);
+                            unsigned miss = 0u;
+#pragma unroll
+                            for (int w = 0; w < RW; ++w) miss |= ((rk_t[w] - rw_s[qi * RW + w]) & rk_g[w]) ^ rk_g[w];
+                            fitbits |= (miss == 0u ? 1u : 0u) << i;
+                        }
+                        const unsigned anyfit = __reduce_or_sync(0xFFFFFFFFu, fitbits);
+                        poss = poss & ((anyfit >> lane) & 1u);
+                    }
                     const unsigned possmask = __ballot_sync(0xFFFFFFFFu, poss);
                     const int n_poss = __popc(possmask);
                     const int my_rank = __popc(possmask & ((1u << lane) - 1u));
@@ -848,7 +882,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
             }
             __syncwarp();
             if (lane == 0) {
-                __threadfence();
+                // a tile in which this stage placed nothing wrote nothing: the release alone carries the upstream
+                // stages' writes forward (release / acquire are cumulative), no fence needed
+                if (n_placed_tile || remote_in) __threadfence();
                 publish(tile + 1);
             }
         }
