@@ -132,6 +132,9 @@ ACSFIT_API acsfit_status acsfit_feasible_mask(acsfit_ctx *ctx, const double *req
  * POD-LIST order (left-to-right float64 sum, no tree reduction).
  *   row_ptr [dev] N+1 int64, run_idx [dev] row_ptr[N] int32 indices into req_run (ascending
  *   inside each node), req_run [dev] R x D, used_inout [dev] N x D (zero = KubeResource()).
+ *   run_idx may be NULL (here, in acsfit_node_states and in the *_host forms): the table is then CONTIGUOUS, the
+ *   pods of node n are rows row_ptr[n] .. row_ptr[n+1] of req_run / flags_run.  That is the layout the host
+ *   layer produces, and it lets K1 / K6 stream the table with bulk copies (csrc/acsfit_stream.cuh).
  */
 ACSFIT_API acsfit_status acsfit_occupancy(acsfit_ctx *ctx, const int64_t *row_ptr, const int32_t *run_idx,
                                const double *req_run, int64_t N, int D, double *used_inout,

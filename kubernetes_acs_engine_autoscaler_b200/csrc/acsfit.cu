@@ -18,6 +18,7 @@
 
 #include "acsfit_kernels.cuh"
 #include "acsfit_rank.cuh"
+#include "acsfit_stream.cuh"
 
 using namespace acsfit;
 
@@ -353,7 +354,7 @@ __global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const in
         bool busy = false, undrainable = false;
         const int64_t k1 = row_ptr[n + 1];
         for (int64_t k = row_ptr[n]; k < k1; ++k) {
-            const int32_t j = run_idx[k];
+            const int64_t j = run_idx ? (int64_t)run_idx[k] : k;
             const uint8_t f = flags_run[j];
             undrainable = undrainable || (f & ACSFIT_PODF_UNDRAINABLE);
             if (f & ACSFIT_PODF_BUSY) {
@@ -601,6 +602,13 @@ static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *
                                       int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
                                       double *used)
 {
+    if (!run_idx) {  // contiguous table: Blackwell bulk copies (acsfit_stream.cuh)
+#define ACSFIT_BULK_ARGS grid, st, row_ptr, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
+        if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_bulk<D, STATES, 2048>(ACSFIT_BULK_ARGS); }
+        if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_bulk<D, STATES, 4096>(ACSFIT_BULK_ARGS); }
+        return launch_node_stream_bulk<D, STATES, 8192>(ACSFIT_BULK_ARGS);
+#undef ACSFIT_BULK_ARGS
+    }
 #define ACSFIT_STREAM_ARGS grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
     if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_b<D, STATES, 2048>(ACSFIT_STREAM_ARGS); }
     if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_b<D, STATES, 4096>(ACSFIT_STREAM_ARGS); }
@@ -2390,7 +2398,7 @@ extern "C" acsfit_status acsfit_occupancy_host(acsfit_ctx *ctx, const int64_t *r
         return fail(ctx, ACSFIT_E_INVALID, "occupancy_host: bad arguments");
     if (N == 0) return ACSFIT_OK;
     const int64_t nnz = row_ptr[N];
-    if (nnz < 0 || (nnz > 0 && !run_idx)) return fail(ctx, ACSFIT_E_INVALID, "occupancy_host: bad CSR");
+    if (nnz < 0) return fail(ctx, ACSFIT_E_INVALID, "occupancy_host: bad CSR");
     TRY(hbuf_reserve(ctx, sizeof(int64_t) * ((size_t)N + 1) + sizeof(int32_t) * (size_t)nnz +
                               sizeof(double) * ((size_t)R * D + (size_t)N * D) + 8 * 256));
     HTAKE(d_ptr, int64_t, (size_t)N + 1);
@@ -2400,8 +2408,8 @@ extern "C" acsfit_status acsfit_occupancy_host(acsfit_ctx *ctx, const int64_t *r
     H2D(d_ptr, row_ptr, sizeof(int64_t) * ((size_t)N + 1));
     H2D(d_req, req_run, sizeof(double) * (size_t)R * D);
     H2D(d_used, used_inout, sizeof(double) * (size_t)N * D);
-    H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
-    TRY(acsfit_occupancy(ctx, d_ptr, d_idx, d_req, N, D, d_used, st));
+    if (run_idx) H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
+    TRY(acsfit_occupancy(ctx, d_ptr, run_idx ? d_idx : nullptr, d_req, N, D, d_used, st));
     D2H(used_inout, d_used, sizeof(double) * (size_t)N * D);
     CUDA_TRY(cudaStreamSynchronize(st));
     return ACSFIT_OK;
@@ -2424,7 +2432,7 @@ extern "C" acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *ro
         return fail(ctx, ACSFIT_E_INVALID, "maintain_host: bad arguments");
     if (N == 0) return ACSFIT_OK;
     const int64_t nnz = row_ptr[N];
-    if (nnz < 0 || (nnz > 0 && !run_idx)) return fail(ctx, ACSFIT_E_INVALID, "maintain_host: bad CSR");
+    if (nnz < 0) return fail(ctx, ACSFIT_E_INVALID, "maintain_host: bad CSR");
     const size_t bytes = sizeof(int64_t) * (2 * (size_t)N + 2) + sizeof(int32_t) * ((size_t)nnz + 2 * (size_t)N) +
                          sizeof(double) * ((size_t)R * D + (size_t)K * D) + (size_t)R + 3 * (size_t)N + 16 * 256;
     TRY(hbuf_reserve(ctx, bytes));
@@ -2445,12 +2453,12 @@ extern "C" acsfit_status acsfit_maintain_host(acsfit_ctx *ctx, const int64_t *ro
     H2D(d_thr, &idle_threshold, sizeof(int64_t));
     H2D(d_req, req_run, sizeof(double) * (size_t)R * D);
     H2D(d_cap, cap_type, sizeof(double) * (size_t)K * D);
-    H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
+    if (run_idx) H2D(d_idx, run_idx, sizeof(int32_t) * (size_t)nnz);
     H2D(d_type, node_type, sizeof(int32_t) * (size_t)N);
     H2D(d_pool, node_pool, sizeof(int32_t) * (size_t)N);
     H2D(d_pflags, flags_run, (size_t)R);
     H2D(d_nflags, node_flags, (size_t)N);
-    TRY(run_node_states(ctx, d_ptr, d_idx, d_req, d_pflags, d_cap, d_type, d_nflags, d_age, N, D, any_pending, d_thr, 1,
+    TRY(run_node_states(ctx, d_ptr, run_idx ? d_idx : nullptr, d_req, d_pflags, d_cap, d_type, d_nflags, d_age, N, D, any_pending, d_thr, 1,
                         d_state, st));
     TRY(arena_reserve(ctx, maintain_scratch(N, T), st));
     ctx->arena_off = 0;

@@ -646,15 +646,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 // bins: bit per lane = the bin already holds a pod (persists over tiles); nodes: threshold is stale
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned touched_tile = 0u;  // nodes / bins of this warp that took a pod in this tile
-                // this lane's node as a packed-rank row (scan thresholds at tile start: what fits it NOW is a subset)
-                unsigned rk_g[RW > 0 ? RW : 1], rk_t[RW > 0 ? RW : 1];
-                if constexpr (RW > 0) {
-#pragma unroll
-                    for (int w = 0; w < RW; ++w) {
-                        rk_g[w] = p.rk.guard[w];
-                        rk_t[w] = (n < Tn ? tw_s[n * RW + w] : 0u) | rk_g[w];
-                    }
-                }
+
                 unsigned ev_local = 0;
                 const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
@@ -712,21 +704,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     bool poss = (testmask >> lane) & 1u;
 #pragma unroll
                     for (int d = 0; d < D; ++d) poss = poss & (own[d] <= Mx[d]);
-                    if constexpr (RW > 0) {
-                        // exact (at tile start) pair test of every entry of the batch against every node of the warp in
-                        // rank space: three integer ops per pair and word.  An entry no node could take at tile start
-                        // can be taken by none now (nodes only fill up): it skips the sequential float64 loop.
-                        unsigned fitbits = 0u;
-                        for (int i = 0; i < n_ent; ++i) {  // warp-uniform trip count
-                            const unsigned qi = __shfl_sync(0xFFFFFFFFu, q_l, i);
-                            unsigned miss = 0u;
-#pragma unroll
-                            for (int w = 0; w < RW; ++w) miss |= ((rk_t[w] - rw_s[qi * RW + w]) & rk_g[w]) ^ rk_g[w];
-                            fitbits |= (miss == 0u ? 1u : 0u) << i;
-                        }
-                        const unsigned anyfit = __reduce_or_sync(0xFFFFFFFFu, fitbits);
-                        poss = poss & ((anyfit >> lane) & 1u);
-                    }
+
                     const unsigned possmask = __ballot_sync(0xFFFFFFFFu, poss);
                     const int n_poss = __popc(possmask);
                     const int my_rank = __popc(possmask & ((1u << lane) - 1u));
@@ -976,7 +954,7 @@ __global__ void occupancy_kernel(const int64_t *__restrict__ row_ptr, const int3
         double acc[kMaxDims];
         for (int d = 0; d < D; ++d) acc[d] = used[(size_t)n * D + d];
         for (int64_t k = row_ptr[n]; k < row_ptr[n + 1]; ++k) {
-            const double *r = req_run + (size_t)run_idx[k] * D;
+            const double *r = req_run + (size_t)(run_idx ? (int64_t)run_idx[k] : k) * D;
             for (int d = 0; d < D; ++d) acc[d] = __dadd_rn(acc[d], r[d]);
         }
         for (int d = 0; d < D; ++d) used[(size_t)n * D + d] = acc[d];

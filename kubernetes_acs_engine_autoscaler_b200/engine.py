@@ -301,7 +301,8 @@ class Engine(object):
         assert isinstance(used, np.ndarray) and used.dtype == np.float64 and used.flags.c_contiguous
         N, D = used.shape
         req_run = _np(req_run, np.float64).reshape(-1, D)
-        self._check(self._lib.acsfit_occupancy_host(self._ctx, _ptr(_np(row_ptr, np.int64)), _ptr(_np(run_idx, np.int32)),
+        self._check(self._lib.acsfit_occupancy_host(self._ctx, _ptr(_np(row_ptr, np.int64)),
+                                                    _ptr(None if run_idx is None else _np(run_idx, np.int32)),
                                                     _ptr(req_run), req_run.shape[0], N, D, _ptr(used)))
         return used
 
@@ -312,7 +313,7 @@ class Engine(object):
         req_run = _np(req_run, np.float64).reshape(-1, D)
         R = req_run.shape[0]
         row_ptr = _np(row_ptr, np.int64)
-        run_idx = _np(run_idx, np.int32)
+        run_idx = None if run_idx is None else _np(run_idx, np.int32)  # None: contiguous table
         flags_run = _np(flags_run, np.uint8)
         node_type = _np(node_type, np.int32)
         node_flags = _np(node_flags, np.uint8)

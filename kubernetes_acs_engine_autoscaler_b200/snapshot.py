@@ -141,14 +141,13 @@ def count_running_pods(nodes, running_pods):
     if not len(run_idx):
         return
     dims = Dims([p.resources for p in running_pods] + [n.used_capacity for n in nodes])
-    req_run = dims.rows(p.resources for p in running_pods)
+    req_run = dims.rows(running_pods[j].resources for j in run_idx)  # rows in node order: a contiguous table
     if (req_run < 0).any() or np.isnan(req_run).any():
         raise ValueError("negative or NaN resource request")
     used = dims.rows(n.used_capacity for n in nodes)
     eng = get_engine()
     d_used = eng.dev(used, torch.float64)
-    eng.occupancy(eng.dev(row_ptr, torch.int64), eng.dev(run_idx, torch.int32), eng.dev(req_run, torch.float64),
-                  d_used)
+    eng.occupancy(eng.dev(row_ptr, torch.int64), None, eng.dev(req_run, torch.float64), d_used)
     used = d_used.cpu().numpy()
     touched = {}
     for n in range(len(nodes)):
@@ -280,7 +279,7 @@ def node_states(nodes, pods_lists, any_pending, idle_threshold):
     age = np.asarray([node_age_seconds(n) for n in nodes], dtype=np.int64)
     eng = get_engine()
     st = eng.node_states(eng.dev(row_ptr, torch.int64),
-                         eng.dev(np.arange(len(flat), dtype=np.int32), torch.int32),
+                         None,  # contiguous table: the rows ARE in node order (bulk-copy streaming kernel)
                          eng.dev(req_run, torch.float64), eng.dev(flags, torch.uint8),
                          eng.dev(cap, torch.float64), eng.dev(node_type, torch.int32),
                          eng.dev(node_flags, torch.uint8), eng.dev(age, torch.int64), any_pending,

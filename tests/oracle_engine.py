@@ -25,7 +25,8 @@ class OracleEngine(object):
 
     def occupancy(self, row_ptr, run_idx, req_run, used):
         u = used.numpy()
-        oracle.occupancy(row_ptr.numpy(), run_idx.numpy(), req_run.numpy(), u)
+        idx = np.arange(req_run.shape[0], dtype=np.int32) if run_idx is None else run_idx.numpy()  # None: contiguous table
+        oracle.occupancy(row_ptr.numpy(), idx, req_run.numpy(), u)
         return used
 
     def first_fit_nodes(self, req, pod_idx, cap_type, node_type, used):
@@ -43,7 +44,8 @@ class OracleEngine(object):
 
     def node_states(self, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age,
                     any_pending, idle_thresholds):
-        st = oracle.node_states(row_ptr.numpy(), run_idx.numpy(), req_run.numpy(), flags_run.numpy(), cap_type.numpy(),
+        idx = np.arange(req_run.shape[0], dtype=np.int32) if run_idx is None else run_idx.numpy()
+        st = oracle.node_states(row_ptr.numpy(), idx, req_run.numpy(), flags_run.numpy(), cap_type.numpy(),
                                 node_type.numpy(), node_flags.numpy(), node_age.numpy(), any_pending, idle_thresholds)
         return torch.from_numpy(st)
 

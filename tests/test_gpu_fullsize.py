@@ -122,6 +122,12 @@ def test_c5_idle_scan_matches_oracle(engine, oracle_mod):
                             engine.dev(c["node_age"], i64), False, thr)
     np.testing.assert_array_equal(to_np(st), st_o)
     assert len(np.unique(st_o)) >= 5
+    # run_idx = NULL: the same table declared contiguous -> the bulk-copy streaming kernel (acsfit_stream.cuh)
+    assert np.array_equal(c["run_idx"], np.arange(len(c["run_idx"])))
+    st_b = engine.node_states(d_ptr, None, d_req, engine.dev(c["flags_run"], u8), engine.dev(c["cap_type"], f64),
+                              engine.dev(c["node_type"], i32), engine.dev(c["node_flags"], u8),
+                              engine.dev(c["node_age"], i64), False, thr)
+    np.testing.assert_array_equal(to_np(st_b), st_o)
     budget = np.array([3, 0, 10 ** 6, -1, 5, 17, 0, 250], dtype=np.int64)
     scal = np.array([1, 1, 1, 1, 0, 1, 1, 1], dtype=np.uint8)
     for dry_run in (True, False):
@@ -135,6 +141,9 @@ def test_c5_idle_scan_matches_oracle(engine, oracle_mod):
     d_used = engine.dev(np.zeros((c["N"], 8)), f64)
     engine.occupancy(d_ptr, d_idx, d_req, d_used)
     np.testing.assert_array_equal(bits(to_np(d_used)), bits(used_o))
+    d_used_b = engine.dev(np.zeros((c["N"], 8)), f64)
+    engine.occupancy(d_ptr, None, d_req, d_used_b)
+    np.testing.assert_array_equal(bits(to_np(d_used_b)), bits(used_o))
     # a shuffled pod list (run_idx is a gather, as in the real host layer) gives the same states
     perm = np.random.default_rng(1).permutation(c["req_run"].shape[0])
     inv = np.empty_like(perm)

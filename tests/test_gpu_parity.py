@@ -325,3 +325,64 @@ def test_chained_launch_timeout_falls_back_unchained(engine, oracle_mod):
     np.testing.assert_array_equal(bits(used_ok), bits(used_fb))
     np.testing.assert_array_equal(r_ok["new_size"], r_fb["new_size"])
     assert r_ok["decisions"] == r_fb["decisions"] and r_ok["n_pending"] == r_fb["n_pending"] > 0
+
+
+@pytest.mark.parametrize("N,D,seed", [(1, 2, 0), (31, 4, 1), (33, 4, 2), (1000, 8, 3), (2049, 16, 4), (70000, 4, 5), (4097, 2, 6),
+                                      (300, 8, 7)])
+def test_streaming_kernels_contiguous_table(engine, oracle_mod, N, D, seed):
+    """K1 / K6 on a CONTIGUOUS running-pod table (run_idx = NULL -> bulk copies + mbarrier, acsfit_stream.cuh):
+    warp ranges that start at any entry offset (chunks are re-aligned to 16 entries), tables whose length is not a
+    multiple of 16 (the last flag bytes take the plain-load path), empty nodes, slices far longer than a chunk,
+    every padded dimension count; the host-buffer calls take the same path."""
+    rng = np.random.default_rng(300 + seed)
+    counts = rng.poisson(7.0, size=N).astype(np.int64)
+    counts[rng.random(N) < 0.25] = 0
+    heavy = rng.integers(0, N, size=max(1, N // 150))
+    counts[heavy] = rng.integers(200, 1200, size=len(heavy))
+    if counts.sum() % 16 == 0:
+        counts[0] += 3                                   # the table length is deliberately not a multiple of 16
+    row_ptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    R = int(row_ptr[-1])
+    req_run = np.zeros((R, D))
+    req_run[:, 0] = rng.integers(1, 400, size=R).astype(np.float64) * 1e-3
+    req_run[:, 1] = rng.integers(1, 64, size=R).astype(np.float64) * float(2 ** 20)
+    if D > 2:
+        req_run[:, 2:] = rng.integers(0, 3, size=(R, D - 2)).astype(np.float64) * (rng.random((R, D - 2)) < 0.3)
+    flags_run = rng.integers(0, 4, size=R).astype(np.uint8)
+    T = 3
+    cap_type = np.zeros((T, D))
+    cap_type[:, 0] = [2.0, 4.0, 8.0]
+    cap_type[:, 1] = [7e9, 14e9, 28e9]
+    cap_type[:, 2:] = 110.0
+    node_type = rng.integers(0, T, size=N).astype(np.int32)
+    node_flags = (rng.random(N) < 0.1).astype(np.uint8)
+    node_age = rng.integers(0, 86400, size=N).astype(np.int64)
+    thr = np.array([60, 900, 3600, 86400], dtype=np.int64)
+    ident = np.arange(R, dtype=np.int32)
+
+    used0 = rng.integers(0, 5, size=(N, D)).astype(np.float64) * 0.125
+    used_o = used0.copy()
+    oracle_mod.occupancy(row_ptr, ident, req_run, used_o)
+    d_used = engine.dev(used0, torch.float64)
+    engine.occupancy(engine.dev(row_ptr, torch.int64), None, engine.dev(req_run, torch.float64), d_used)
+    np.testing.assert_array_equal(bits(to_np(d_used)), bits(used_o))
+    used_h = used0.copy()
+    engine.occupancy_host(row_ptr, None, req_run, used_h)
+    np.testing.assert_array_equal(bits(used_h), bits(used_o))
+
+    for any_pending in (False, True):
+        st_o = oracle_mod.node_states(row_ptr, ident, req_run, flags_run, cap_type, node_type, node_flags, node_age,
+                                      any_pending, thr)
+        st = engine.node_states(engine.dev(row_ptr, torch.int64), None, engine.dev(req_run, torch.float64),
+                                engine.dev(flags_run, torch.uint8), engine.dev(cap_type, torch.float64),
+                                engine.dev(node_type, torch.int32), engine.dev(node_flags, torch.uint8),
+                                engine.dev(node_age, torch.int64), any_pending, thr)
+        np.testing.assert_array_equal(to_np(st), st_o)
+    node_pool = node_type.copy()
+    budget = np.array([2, 0, 7], dtype=np.int64)
+    s_o, a_o = oracle_mod.maintain_actions(st_o[1].copy(), node_pool, budget, np.ones(T, np.uint8), True)
+    s_h, a_h = engine.maintain_host(row_ptr, None, req_run, flags_run, cap_type, node_type, node_flags, node_age,
+                                    node_pool, True, 900, budget, np.ones(T, np.uint8), True)
+    np.testing.assert_array_equal(s_h, s_o)
+    np.testing.assert_array_equal(a_h, a_o)

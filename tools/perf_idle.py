@@ -25,9 +25,12 @@ def main():
     c = syn.make_idle_cluster(args.N, args.D, args.T, seed=5)
     R = c["req_run"].shape[0]
     i64, i32, f64, u8 = torch.int64, torch.int32, torch.float64, torch.uint8
+    ap_gather = os.environ.get("ACSFIT_IDLE_GATHER") == "1"   # 1: pass the index list (gather kernel) instead of NULL
     d = {k: eng.dev(c[k], t) for k, t in (("row_ptr", i64), ("run_idx", i32), ("req_run", f64), ("flags_run", u8),
                                           ("cap_type", f64), ("node_type", i32), ("node_flags", u8), ("node_age", i64),
                                           ("node_pool", i32))}
+    if not ap_gather:
+        d["run_idx"] = None  # contiguous table: the bulk-copy streaming kernel
     thr = np.array([60, 300, 900, 1800, 3600, 7200, 21600, 86400][:args.S], dtype=np.int64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
 
@@ -47,7 +50,7 @@ def main():
     D, N, S = args.D, args.N, args.S
     t, st = timed(lambda: eng.node_states(d["row_ptr"], d["run_idx"], d["req_run"], d["flags_run"], d["cap_type"],
                                           d["node_type"], d["node_flags"], d["node_age"], False, thr))
-    bytes_states = R * (8 * D + 1 + 4) + N * (8 + 4 + 1 + 8) + S * N
+    bytes_states = R * (8 * D + 1 + (4 if ap_gather else 0)) + N * (8 + 4 + 1 + 8) + S * N
     print("node_states: N=%d R=%d D=%d S=%d: %.3f ms, %.1f GB/s algorithmic (%.1f MB)" % (N, R, D, S, t, bytes_states / t / 1e6, bytes_states / 1e6))
     budget = c["pool_actual"].astype(np.int64) - 1
     for dry in (True, False):
@@ -56,7 +59,7 @@ def main():
         print("maintain_actions dry_run=%s: %.3f ms (%.1f GB/s over %d B/node)" % (dry, t, N * 6 / t / 1e6, 6))
     used = torch.zeros((N, D), dtype=f64, device=eng.device)
     t, _ = timed(lambda: eng.occupancy(d["row_ptr"], d["run_idx"], d["req_run"], used.zero_()))
-    bytes_occ = R * (8 * D + 4) + N * (8 + 16 * D)
+    bytes_occ = R * (8 * D + (4 if ap_gather else 0)) + N * (8 + 16 * D)
     print("occupancy: %.3f ms, %.1f GB/s algorithmic" % (t, bytes_occ / t / 1e6))
 
 
