@@ -1,0 +1,90 @@
+"""log / notification aggregation.  At fixture scale the product's log text equals the
+reference's line for line (the recorded ticks check that); beyond LOG_DETAIL_LIMIT pods the per-pod lines are
+replaced by counts, and the notifier aggregates the same way."""
+import logging
+import types
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+
+class _Res(dict):
+    pass
+
+
+def _pod(i, cpu="1500m"):
+    return {"metadata": {"name": "p%d" % i, "namespace": "ns", "uid": "u%d" % i, "creationTimestamp": "2026-09-21T07:00:00Z"},
+            "spec": {"containers": [{"name": "c", "resources": {"requests": {"cpu": cpu}}}]}, "status": {"phase": "Pending"}}
+
+
+def _node(i):
+    return {"metadata": {"name": "k8s-agentpool1-16334397-%d" % i, "creationTimestamp": "2026-09-20T07:00:00Z",
+                         "labels": {"beta.kubernetes.io/instance-type": "Standard_D2_v2",
+                                    "failure-domain.beta.kubernetes.io/region": "southcentralus"}}, "spec": {}}
+
+
+@pytest.fixture()
+def host(tmp_path, monkeypatch, oracle_mod):
+    from kubernetes_acs_engine_autoscaler_b200 import capacity, snapshot
+    from oracle_engine import OracleEngine
+    capacity.load(gu.write_capacity_file(tmp_path), cpu_reserve=0.0)
+    monkeypatch.setattr(snapshot, "_engine", OracleEngine())
+    return monkeypatch
+
+
+def test_get_pending_pods_summarises_beyond_the_detail_limit(host, caplog):
+    from kubernetes_acs_engine_autoscaler_b200 import capacity, cluster as cl
+    from kubernetes_acs_engine_autoscaler_b200.kube import KubeNode, KubePod
+    j = []
+    nodes = []
+    for i in range(3):
+        n = KubeNode(gu.FakeKubeObject(_node(i), j, "node"))
+        n.capacity = capacity.get_capacity_for_instance_type(n.instance_type)
+        nodes.append(n)
+    pods = [KubePod(gu.FakeKubeObject(_pod(i), j, "pod")) for i in range(12)]
+    c = cl.Cluster(None, 1800, 1, "a", "b", "c", "d", "e", "f", 600, "rg", None, "", dry_run=True)
+    with caplog.at_level(logging.DEBUG, logger="autoscaler"):
+        pending = c.get_pending_pods(pods, nodes)            # 12 pods <= limit: the reference's per-pod lines
+    detail = [r.getMessage() for r in caplog.records]
+    assert len(pending) == 9 and sum(" fits on " in m for m in detail) == 3 and "Pending pods: 9" in detail
+    assert sum(m.startswith("p") and len(m) <= 3 for m in detail) == 9   # the pending pods' names at DEBUG
+    for n in nodes:
+        n.used_capacity = type(n.used_capacity)()
+    caplog.clear()
+    host.setattr(cl, "LOG_DETAIL_LIMIT", 10)
+    with caplog.at_level(logging.DEBUG, logger="autoscaler"):
+        pending2 = c.get_pending_pods(pods, nodes)           # 12 pods > limit 10: counts only
+    summary = [r.getMessage() for r in caplog.records]
+    assert [p.uid for p in pending2] == [p.uid for p in pending]
+    assert summary == ["3 pods fit on existing nodes", "Pending pods: 9"]
+
+
+def test_notifier_messages_and_aggregation():
+    from kubernetes_acs_engine_autoscaler_b200 import notification as nt
+    pods = [types.SimpleNamespace(namespace="ns", name="p%d" % i, uid="u%d" % i, selectors={}) for i in range(9)]
+    assert nt.pod_string(pods[:2]) == "ns/p0, ns/p1"
+    assert nt.pod_string(pods[:5]) == "ns/p0, ns/p1, ns/p2, ns/p3, ns/p4"
+    assert nt.pod_string(pods) == "ns/p0, ns/p1, ns/p2, ns/p3, and 5 others"   # notification.py:33-40
+    sent = []
+    n = nt.Notifier(hook="http://hook", post=lambda url, json=None: sent.append((url, json)) or types.SimpleNamespace(text="ok"),
+                    detail_limit=3)
+    records = []
+    handler = logging.Handler()
+    handler.emit = records.append
+    nt.struct_logger.addHandler(handler)
+    nt.struct_logger.setLevel(logging.DEBUG)
+    try:
+        n.notify_scale({"a": 7}, pods, {"a": 2})
+    finally:
+        nt.struct_logger.removeHandler(handler)
+    assert sent == [("http://hook", {"text": "Scaled up from {'a': 2} to new capacity {'a': 7}\n"
+                                             "Change triggered by ns/p0, ns/p1, ns/p2, ns/p3, and 5 others",
+                                     "username": "kubernetes-acs-engine-autoscaler", "icon_emoji": ":camel:"})]
+    assert [r.getMessage() for r in records] == ["scale"] * 3 + ["scale (summary)"]
+    assert records[0].pod_name == "ns/p0" and records[3].pods_not_listed == 6 and records[3].units_requested == {"a": 7}
+    quiet = nt.Notifier(hook=None, post=lambda *a, **k: (_ for _ in ()).throw(AssertionError("no hook, no post")))
+    quiet.notify_drained_node("node-1", pods[:2])
+    n2 = nt.Notifier(hook="h", post=lambda url, json=None: (_ for _ in ()).throw(RuntimeError("down")))
+    n2.notify_drained_node("node-1", pods[:2])    # a failing chat hook never fails the tick
