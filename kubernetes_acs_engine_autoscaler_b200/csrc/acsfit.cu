@@ -602,13 +602,9 @@ static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *
                                       int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
                                       double *used)
 {
-    if (!run_idx) {  // contiguous table: Blackwell bulk copies (acsfit_stream.cuh)
-#define ACSFIT_BULK_ARGS grid, st, row_ptr, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
-        if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_bulk<D, STATES, 2048>(ACSFIT_BULK_ARGS); }
-        if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_bulk<D, STATES, 4096>(ACSFIT_BULK_ARGS); }
-        return launch_node_stream_bulk<D, STATES, 8192>(ACSFIT_BULK_ARGS);
-#undef ACSFIT_BULK_ARGS
-    }
+    if (!run_idx)  // contiguous table: Blackwell bulk copies (acsfit_stream.cuh)
+        return launch_node_stream_bulk<D, STATES, kBulkBytesPerWarp>(grid, st, row_ptr, req_run, flags_run, cap_type, node_type,
+                                                                     node_flags, node_age, N, any_pending, thr, S, out_state, used);
 #define ACSFIT_STREAM_ARGS grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
     if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_b<D, STATES, 2048>(ACSFIT_STREAM_ARGS); }
     if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_b<D, STATES, 4096>(ACSFIT_STREAM_ARGS); }

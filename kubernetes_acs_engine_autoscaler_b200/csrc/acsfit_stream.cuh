@@ -18,7 +18,13 @@
 
 namespace acsfit {
 
-constexpr int kBulkWarps = 8;
+// Lane = node: a warp is only fully busy while the chunk in shared memory holds entries of all 32 nodes of the
+// group it is summing.  With ~10 running pods per node that takes >= 320 entries per chunk, so the chunks are
+// large (16 KB per buffer, two buffers per warp) and the CTA has few warps: 6 x 32 KB = 192 KB of staging per SM,
+// all of it in flight.  (ncu of the first version, 4 KB chunks and 8 warps: 6 of 32 lanes active on average in
+// the consume loop, 60 % of the issue slots busy at 0.55 of the HBM peak -- issue-bound on idle lanes.)
+constexpr int kBulkWarps = 6;
+constexpr int kBulkBytesPerWarp = 32768;
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
@@ -106,15 +112,24 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
     int64_t lo, hi, lo_n = 0, hi_n = 0;
     double acc[D], acc_n[D];
     bool busy = false, undrainable = false;
-    auto fetch_group = [&](int64_t gg, int64_t &l, int64_t &h, double (&a0)[D]) {
+    // per-node inputs of the state decision, fetched a group ahead like the row pointers (no exposed latency)
+    int32_t ntype = 0, ntype_n = 0;
+    uint8_t nflags = 0, nflags_n = 0;
+    int64_t nage = 0, nage_n = 0;
+    auto fetch_group = [&](int64_t gg, int64_t &l, int64_t &h, double (&a0)[D], int32_t &ty, uint8_t &fl, int64_t &ag) {
         const int64_t nn = gg * 32 + lane;
         l = row_ptr[min(nn, N)];
         h = row_ptr[min(nn + 1, N)];  // lanes past N get an empty range
 #pragma unroll
         for (int d = 0; d < D; ++d) a0[d] = (!STATES && nn < N) ? used_inout[(size_t)nn * D + d] : 0.0;
+        if (STATES && nn < N) {
+            ty = node_type[nn];
+            fl = node_flags[nn];
+            ag = node_age[nn];
+        }
     };
-    fetch_group(g0, lo, hi, acc);
-    if (g0 + 1 < g1) fetch_group(g0 + 1, lo_n, hi_n, acc_n);
+    fetch_group(g0, lo, hi, acc, ntype, nflags, nage);
+    if (g0 + 1 < g1) fetch_group(g0 + 1, lo_n, hi_n, acc_n, ntype_n, nflags_n, nage_n);
     int64_t group_end = __shfl_sync(0xFFFFFFFFu, hi, 31);
 
     auto finalize = [&]() {
@@ -125,7 +140,7 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
             for (int d = 0; d < D; ++d) used_inout[(size_t)n * D + d] = acc[d];
             return;
         }
-        const double *cap = cap_type + (size_t)node_type[n] * D;
+        const double *cap = cap_type + (size_t)ntype * D;
         bool under = true;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -133,8 +148,8 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
             const double left = __dsub_rn(__dmul_rn(cap[d], 0.3), acc[d]);
             under = under && (left >= 0.0);
         }
-        const bool unsched = node_flags[n] & ACSFIT_NODEF_UNSCHEDULABLE;
-        const int64_t age = node_age[n];
+        const bool unsched = nflags & ACSFIT_NODEF_UNSCHEDULABLE;
+        const int64_t age = nage;
         for (int s = 0; s < S; ++s) {
             uint8_t st;
             if (busy && !under) st = unsched ? ACSFIT_ST_BUSY_UNSCHEDULABLE : ACSFIT_ST_BUSY;
@@ -164,9 +179,8 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
         const uint8_t *flags_b = flags_s + buf * kChunk;
         while (g < g1) {
             if (has_chunk) {
-                const int64_t a = max(lo, kc), b = min(hi, chunk_end);
-                for (int64_t k = a; k < b; ++k) {
-                    const int e = (int)(k - kc);
+                const int ea = (int)(max(lo, kc) - kc), eb = (int)(min(hi, chunk_end) - kc);
+                for (int e = ea; e < eb; ++e) {
                     bool take = true;
                     if (STATES) {
                         const uint8_t f = flags_b[e];
@@ -191,10 +205,13 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
             hi = hi_n;
 #pragma unroll
             for (int d = 0; d < D; ++d) acc[d] = acc_n[d];
+            ntype = ntype_n;
+            nflags = nflags_n;
+            nage = nage_n;
             busy = false;
             undrainable = false;
             group_end = __shfl_sync(0xFFFFFFFFu, hi, 31);
-            if (g + 1 < g1) fetch_group(g + 1, lo_n, hi_n, acc_n);
+            if (g + 1 < g1) fetch_group(g + 1, lo_n, hi_n, acc_n, ntype_n, nflags_n, nage_n);
         }
         if (g >= g1) break;
         __syncwarp();  // every lane is done with this buffer before it is refilled
