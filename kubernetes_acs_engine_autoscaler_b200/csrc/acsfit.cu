@@ -391,6 +391,7 @@ __global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const in
 // entries in order.  The ordered left-to-right float64 sum of the reference is preserved; only the memory
 // access pattern changes (coalesced streaming instead of one scattered row per thread).
 constexpr int kStreamWarps = 8;
+static int g_bulk_cfg = 1;        // geometry of the bulk-copy form (developer knob ACSFIT_BULK_CFG)
 static int g_stream_bytes = 8192;  // staging bytes per warp (developer knob ACSFIT_STREAM_BYTES: 2048 / 4096 / 8192)
 
 template <int D, bool STATES, int kStreamBytesPerWarp>
@@ -602,9 +603,22 @@ static cudaError_t launch_node_stream(int grid, cudaStream_t st, const int64_t *
                                       int64_t N, int any_pending, const int64_t *thr, int S, uint8_t *out_state,
                                       double *used)
 {
-    if (!run_idx)  // contiguous table: Blackwell bulk copies (acsfit_stream.cuh)
-        return launch_node_stream_bulk<D, STATES, kBulkBytesPerWarp>(grid, st, row_ptr, req_run, flags_run, cap_type, node_type,
-                                                                     node_flags, node_age, N, any_pending, thr, S, out_state, used);
+    if (!run_idx) {  // contiguous table: Blackwell bulk copies (acsfit_stream.cuh); geometry = <bytes per warp, warps>
+#define ACSFIT_BULK_ARGS grid, st, row_ptr, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
+        if constexpr (D <= 8) {
+            switch (g_bulk_cfg) {
+            case 1: return launch_node_stream_bulk<D, STATES, 16384, 12>(ACSFIT_BULK_ARGS);
+            case 2: return launch_node_stream_bulk<D, STATES, 16384, 8>(ACSFIT_BULK_ARGS);
+            case 3: return launch_node_stream_bulk<D, STATES, 32768, 6>(ACSFIT_BULK_ARGS);
+            case 4: return launch_node_stream_bulk<D, STATES, 8192, 16>(ACSFIT_BULK_ARGS);
+            case 0: return launch_node_stream_bulk<D, STATES, 8192, 8>(ACSFIT_BULK_ARGS);
+            default: return launch_node_stream_bulk<D, STATES, 16384, 12>(ACSFIT_BULK_ARGS);  // measured best (profiles/r02_summary.md)
+            }
+        } else {
+            return launch_node_stream_bulk<D, STATES, 16384, 8>(ACSFIT_BULK_ARGS);
+        }
+#undef ACSFIT_BULK_ARGS
+    }
 #define ACSFIT_STREAM_ARGS grid, st, row_ptr, run_idx, req_run, flags_run, cap_type, node_type, node_flags, node_age, N, any_pending, thr, S, out_state, used
     if constexpr (D <= 4) { if (g_stream_bytes <= 2048) return launch_node_stream_b<D, STATES, 2048>(ACSFIT_STREAM_ARGS); }
     if constexpr (D <= 8) { if (g_stream_bytes <= 4096) return launch_node_stream_b<D, STATES, 4096>(ACSFIT_STREAM_ARGS); }
@@ -750,6 +764,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     memset(&ctx->rk, 0, sizeof ctx->rk);
     if (const char *env = getenv("ACSFIT_MIN_STAGES")) ctx->min_stages = std::max(0, atoi(env));
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
+    if (const char *env = getenv("ACSFIT_BULK_CFG")) g_bulk_cfg = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {

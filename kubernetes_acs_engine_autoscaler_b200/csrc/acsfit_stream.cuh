@@ -23,8 +23,8 @@ namespace acsfit {
 // large (16 KB per buffer, two buffers per warp) and the CTA has few warps: 6 x 32 KB = 192 KB of staging per SM,
 // all of it in flight.  (ncu of the first version, 4 KB chunks and 8 warps: 6 of 32 lanes active on average in
 // the consume loop, 60 % of the issue slots busy at 0.55 of the HBM peak -- issue-bound on idle lanes.)
-constexpr int kBulkWarps = 6;
-constexpr int kBulkBytesPerWarp = 32768;
+// The two pull against each other (fewer warps hide less latency), so the geometry is a template pair
+// <warps per CTA, staging bytes per warp> chosen per kernel from measurements (profiles/r02_summary.md).
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     } while (!done);
 }
 
-template <int D, bool STATES, int kBytesPerWarp>
+template <int D, bool STATES, int kBytesPerWarp, int kBulkWarps>
 __global__ void __launch_bounds__(kBulkWarps * 32)
 node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__restrict__ req_run,
                         const uint8_t *__restrict__ flags_run, const double *__restrict__ cap_type,
@@ -219,7 +219,7 @@ node_stream_bulk_kernel(const int64_t *__restrict__ row_ptr, const double *__res
     }
 }
 
-template <int D, bool STATES, int kBytesPerWarp>
+template <int D, bool STATES, int kBytesPerWarp, int kBulkWarps>
 static cudaError_t launch_node_stream_bulk(int grid, cudaStream_t st, const int64_t *row_ptr, const double *req_run,
                                            const uint8_t *flags_run, const double *cap_type, const int32_t *node_type,
                                            const uint8_t *node_flags, const int64_t *node_age, int64_t N, int any_pending,
@@ -227,13 +227,13 @@ static cudaError_t launch_node_stream_bulk(int grid, cudaStream_t st, const int6
 {
     constexpr int kChunk = kBytesPerWarp / 2 / (8 * D);
     const size_t smem = (size_t)kBulkWarps * kBytesPerWarp + (size_t)kBulkWarps * 2 * kChunk + (size_t)kBulkWarps * 2 * sizeof(uint64_t);
-    auto kern = node_stream_bulk_kernel<D, STATES, kBytesPerWarp>;
+    auto kern = node_stream_bulk_kernel<D, STATES, kBytesPerWarp, kBulkWarps>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, dev = 0, sms = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBulkWarps * 32, smem) == cudaSuccess && per_sm > 0 &&
         cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
-        grid = std::min(grid, per_sm * sms);
+        grid = per_sm * sms;  // persistent: exactly the resident CTAs (each warp takes a contiguous range of groups)
     kern<<<grid, kBulkWarps * 32, smem, st>>>(row_ptr, req_run, flags_run, cap_type, node_type, node_flags, node_age, N,
                                               any_pending, thr, S, out_state, used);
     return cudaGetLastError();
