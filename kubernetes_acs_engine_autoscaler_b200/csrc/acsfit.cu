@@ -391,6 +391,7 @@ __global__ void node_states_kernel(const int64_t *__restrict__ row_ptr, const in
 // entries in order.  The ordered left-to-right float64 sum of the reference is preserved; only the memory
 // access pattern changes (coalesced streaming instead of one scattered row per thread).
 constexpr int kStreamWarps = 8;
+static int g_trace = 0;           // ACSFIT_TRACE=1: per-pass timings on stderr (with acsfit_ctx_set_timing)
 static int g_bulk_cfg = 1;        // geometry of the bulk-copy form (developer knob ACSFIT_BULK_CFG)
 static int g_stream_bytes = 8192;  // staging bytes per warp (developer knob ACSFIT_STREAM_BYTES: 2048 / 4096 / 8192)
 
@@ -765,6 +766,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     if (const char *env = getenv("ACSFIT_MIN_STAGES")) ctx->min_stages = std::max(0, atoi(env));
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
     if (const char *env = getenv("ACSFIT_BULK_CFG")) g_bulk_cfg = atoi(env);
+    if (const char *env = getenv("ACSFIT_TRACE")) g_trace = atoi(env);
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -1469,6 +1471,8 @@ static acsfit_status cluster_first_fit(acsfit_ctx *ctx, const double *req, const
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->last_ms += ms;
+        if (g_trace) fprintf(stderr, "[acsfit r%d] cluster nodes pass: %lld pods, %d stages x %d nodes, %d block(s): %.3f ms\n",
+                             ctx->rank, (long long)F, my_stages, Tn, blocks, ms);
         if (decisions_dev) {
             unsigned long long d = 0;
             CUDA_TRY(cudaMemcpy(&d, decisions_dev, sizeof d, cudaMemcpyDeviceToHost));
@@ -1554,6 +1558,7 @@ static acsfit_status first_fit_impl(acsfit_ctx *ctx, const double *req, const in
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->last_ms += ms;
+        if (g_trace) fprintf(stderr, "[acsfit] nodes pass: %lld pods, %d stages x %d nodes: %.3f ms\n", (long long)P, plan.stages, plan.Tn, ms);
         if (out_decisions) {
             unsigned long long d = 0;
             CUDA_TRY(cudaMemcpy(&d, out_decisions, sizeof d, cudaMemcpyDeviceToHost));
@@ -1730,6 +1735,8 @@ static acsfit_status fulfill_impl(acsfit_ctx *ctx, const double *req, const int3
                     float ms = 0.f;
                     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
                     total_ms += ms;
+                    if (g_trace) fprintf(stderr, "[acsfit r%d] bins pass: pool %d, %lld pods, %d stages x %d bins, base %lld: %.3f ms\n",
+                                         ctx->rank, t, (long long)M, plan.stages, plan.Tn, (long long)bin_base, ms);
                 }
                 ctx->last_stages += plan.stages;
                 ctx->last_tiles += pp.num_tiles;

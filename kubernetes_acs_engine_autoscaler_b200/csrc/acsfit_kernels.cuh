@@ -45,6 +45,7 @@ constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
 constexpr int kMinBatch = 4;  // entries a consumer warp waits for before it starts a batch
 constexpr int kMaxDims = 16;
+constexpr int kRing = 8;      // tiles whose alive words a stage fetches in one go once its upstream is that far ahead
 
 // Packed-rank form of the scan predicate ("rank compression").  Per resource dimension d the
 // distinct request values of this tick's pod table are sorted; a pod's request is replaced by r' = 1 + its rank,
@@ -176,7 +177,7 @@ struct PipelineSmem {
     {
         return sizeof(double) * ((size_t)kTile * D + (size_t)(BINS ? 1 : 3) * D * Tn + (size_t)NW * 36 * D /*batch rows*/ + (PRUNE ? (size_t)(NW + 1) * D : 0) /*warp bounds + stage bound*/)
                + sizeof(unsigned) * (kTile /*cand*/ + kTile / 32 /*hit*/ + kTile / 32 /*alive*/ + NW /*opened*/ +
-                                     NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + 8 /*next alive words*/ + (kTile + 1) /*hitlist*/ +
+                                     NW /*dirty*/ + 8 /*scan counts*/ + 8 /*alive counts*/ + 8 /*misc*/ + kRing * 8 /*alive words of the next tiles*/ + (kTile + 1) /*hitlist*/ +
                                      (NW - 1) * (kTile + 1) /*warp queues*/ + 1 /*pad*/)
                + sizeof(unsigned short) * kTile /*slot_of*/ + (size_t)NW * 32 /*accepted node per dense entry*/
                + sizeof(unsigned) * ((size_t)RW * Tn /*packed node words*/ + (size_t)RW * kTile /*packed pod words*/ + 4 /*alignment*/);
@@ -232,8 +233,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
     unsigned *wcount = dirty + NW;                              // [8] pods to scan per tile word
     unsigned *acount = wcount + 8;                              // [8] alive pods per tile word
     unsigned *misc = acount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
-    unsigned *nextw = misc + 8;                                 // [8] alive words of the tile about to be loaded
-    unsigned *hitlist = nextw + 8;                              // [kTile+1] ordered hit entries (q+1), then kQueueEnd
+    unsigned *nextw = misc + 8;                                 // [kRing][8] alive words of the next tiles (ring, slot = tile % kRing)
+    unsigned *hitlist = nextw + kRing * 8;                      // [kTile+1] ordered hit entries (q+1), then kQueueEnd
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
     unsigned short *slot_of = reinterpret_cast<unsigned short *>(queue + (NW - 1) * (kTile + 1) + 1);  // [kTile]
     unsigned char *found_s = reinterpret_cast<unsigned char *>(slot_of + kTile);  // [NW][32] node that took dense entry k
@@ -374,6 +375,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
     };
     prefetch_row(0);
+    int known = 0, ring_hi = 0;  // (warp 1) tiles the upstream is known to have published / whose alive words are in the ring
 
     for (int tile = 0; tile < p.num_tiles; ++tile) {
         if (p.prof && tid == 0) tp = clock64();
@@ -381,32 +383,45 @@ firstfit_pipeline_kernel(const PipelineParams p)
         //      can still be publishing the previous tile) ---------------------------------------
         //      The same warp then fetches the tile's alive words, so that their L2 (or NVLink) latency is
         //      paid while the other warps are still finishing the previous tile, not after the barrier.
+        //      The upstream counter is re-read only when this stage has caught up with what it last saw, and the
+        //      alive words of every tile known to be published (up to kRing ahead) are fetched in one go: a stage
+        //      that lags its upstream -- always the case across NVLink, where one poll costs microseconds -- pays
+        //      the hand-off latency once per kRing tiles instead of once per tile.
         if (warp == 1) {
-            if ((stage > 0 || p.upstream) && lane == 0) {
-                const int *flag = stage > 0 ? p.progress + (stage - 1) : p.upstream;
-                unsigned spins = 0;
-                if (stage > 0 && *(volatile int *)p.drained) {
-                    // an earlier stage finished with nothing left alive: every remaining tile is empty
-                    misc[2] = 1;
-                } else
-                while ((p.sys_scope && stage == 0 ? ld_acquire_sys(flag) : ld_acquire(flag)) <= tile) {
-                    if ((++spins & 63u) == 0) {
-                        if (*(volatile int *)p.status != 0 ||
-                            global_timer_ns() - t_start > p.watchdog_ns) {
-                            atomicExch(p.status, 1);
-                            misc[1] = 1;
-                            break;
+            if (known <= tile) {  // (known / ring_hi are warp-uniform registers of warp 1)
+                int seen = known;
+                if (lane == 0) {
+                    if (!(stage > 0 || p.upstream)) {
+                        seen = p.num_tiles;  // the head of the pipeline: every tile is there from the start
+                    } else if (stage > 0 && *(volatile int *)p.drained) {
+                        misc[2] = 1;  // an earlier stage finished with nothing left alive: every remaining tile is empty
+                    } else {
+                        const int *flag = stage > 0 ? p.progress + (stage - 1) : p.upstream;
+                        unsigned spins = 0;
+                        while ((seen = (p.sys_scope && stage == 0 ? ld_acquire_sys(flag) : ld_acquire(flag))) <= tile) {
+                            if ((++spins & 63u) == 0) {
+                                if (*(volatile int *)p.status != 0 || global_timer_ns() - t_start > p.watchdog_ns) {
+                                    atomicExch(p.status, 1);
+                                    misc[1] = 1;
+                                    break;
+                                }
+                            }
+                            __nanosleep(20);
                         }
                     }
-                    __nanosleep(20);
                 }
+                known = __shfl_sync(0xFFFFFFFFu, seen, 0);  // also orders the loads below after lane 0's acquire
             }
-            __syncwarp();  // the acquire above orders the loads below (all lanes of this warp)
-            if (lane < kTile / 32) {
-                const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + lane;
-                unsigned w = 0u;
-                if (wj * 32 < p.M) w = remote_in ? ld_relaxed_sys_u32(p.alive_in + wj) : __ldcg(p.alive + wj);
-                nextw[lane] = w;
+            if (tile >= ring_hi && known > tile) {  // refill: tiles [tile, min(known, tile + kRing))
+                const int hi_t = min(known, tile + kRing);
+                for (int i = lane; i < (hi_t - tile) * (kTile / 32); i += 32) {
+                    const int t = tile + i / (kTile / 32);
+                    const int64_t wj = (int64_t)(p.tile_lo + t) * (kTile / 32) + (i % (kTile / 32));
+                    unsigned w = 0u;
+                    if (wj * 32 < p.M) w = remote_in ? ld_relaxed_sys_u32(p.alive_in + wj) : __ldcg(p.alive + wj);
+                    nextw[(t % kRing) * (kTile / 32) + (i % (kTile / 32))] = w;
+                }
+                ring_hi = hi_t;
             }
         }
         __syncthreads();  // (S1) previous tile fully retired (publish included), poll result and alive words visible
@@ -416,7 +431,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
 
         // ---- load the tile: compact the alive pods' rows into shared memory ----------------
         const int64_t j = (int64_t)(p.tile_lo + tile) * kTile + tid;
-        const unsigned word = nextw[warp];
+        const unsigned word = nextw[(tile % kRing) * (kTile / 32) + warp];
         const bool is_alive = (word >> lane) & 1u;
         bool pass = is_alive;
         if (PRUNE && is_alive) {  // can the pod fit any node of the stage at all?  (per-dimension bound over the warps)
