@@ -343,21 +343,31 @@ def timed(step_fn, steps, warmup, flush, barrier, launch_count):
     return res, sum(a.elapsed_time(b) for a, b in ev), launch_count() - l0
 
 
-def physical_roofline(kernel_dec_per_s, nw, sm_mhz, sms=148):
-    """what the candidate scan is bound by: integer issue.  A pair costs 2 ops per packed word + 1 compare
-    (acsfit_kernels.cuh: subtract, three-input logic, compare) on 128 int32 lanes per clock and SM
-    (tools/ubench6.cu measures the rate); credited decisions ~ pairs tested."""
+INT_LANE_OPS_PER_CLK_SM = 77.0  # measured: tools/ubench6.cu, profiles/r02b_ubench6.txt (IADD + LOP3 mix, all SMs busy)
+
+
+def physical_roofline(kernel_dec_per_s, nw, sm_mhz, kernel_ms=None, placements=None, sms=148):
+    """what actually bounds the pipeline.  (1) The candidate scan is integer-issue work: a pair costs 2 ops per packed
+    word + 1 compare (acsfit_kernels.cuh) at the measured int32 issue rate; credited decisions ~ pairs tested.
+    (2) Below that ceiling sits the sequential placement chain: first fit is a recurrence, every placement waits for
+    the previous one on the frontier warp -- reported as kernel time per placement."""
     if not sm_mhz:
         return None
-    ops = 2 * max(nw, 1) + 1 if nw else None
-    if ops is None:
-        return {"limiter": "fp64 compare issue (float64 scan: D DSETP per pair, ~45 lane-ops/clk/SM, tools/ubench5.cu)",
-                "achieved": kernel_dec_per_s, "unit": UNIT}
-    ceiling = sms * 128.0 * sm_mhz * 1e6 / ops
-    return {"limiter": "int32 issue of the packed-rank scan (%d ops per pair at %d word(s) per row); below it: the "
-                       "sequential placement chain (DESIGN.md section 6)" % (ops, nw),
-            "achieved": kernel_dec_per_s, "ceiling": ceiling, "unit": UNIT, "frac": kernel_dec_per_s / ceiling,
-            "source": "tools/ubench6.cu (int32 lanes/clk/SM) x SM clock under load"}
+    out = {"achieved": kernel_dec_per_s, "unit": UNIT}
+    if nw:
+        ops = 2 * nw + 1
+        out["limiter"] = ("the sequential placement chain (see chain_ns_per_placement; a placing step costs ~110-260 cycles "
+                          "on the frontier warp and nothing else can proceed past it); the scan's own ceiling is int32 "
+                          "issue: %d ops per pair at %d packed word(s) per row" % (ops, nw))
+        out["ceiling"] = sms * INT_LANE_OPS_PER_CLK_SM * sm_mhz * 1e6 / ops
+        out["frac"] = kernel_dec_per_s / out["ceiling"]
+        out["source"] = "tools/ubench6.cu: %.0f int32 lane-ops/clk/SM (profiles/r02b_ubench6.txt) x SM clock under load" % INT_LANE_OPS_PER_CLK_SM
+    else:
+        out["limiter"] = "fp64 compare issue (float64 scan: D DSETP per pair, ~45 lane-ops/clk/SM, tools/ubench5.cu) and the placement chain"
+    if kernel_ms and placements:
+        out["chain_ns_per_placement"] = kernel_ms * 1e6 / placements
+        out["placements_per_step"] = int(placements)
+    return out
 
 
 def sub_record_c3(eng, syn, flush, steps, peak):
@@ -430,6 +440,56 @@ def sub_record_c5(eng, syn, flush, peak):
     return out
 
 
+def python_surface(eng, syn, c, reps=3):
+    """the tick through the reference's own entry point: Cluster.loop_logic (alias scale_loop) fed kube-API style
+    dicts for every node and pod of the snapshot -- object construction, flattening, the GPU path and the log /
+    hand-off code all inside the timed region (host-side ingestion)."""
+    import logging
+    from kubernetes_acs_engine_autoscaler_b200 import agent_pool, snapshot
+    from kubernetes_acs_engine_autoscaler_b200.cluster import Cluster
+
+    class Obj(object):
+        __slots__ = ("obj",)
+
+        def __init__(self, o):
+            self.obj = o
+
+        @property
+        def name(self):
+            return self.obj["metadata"]["name"]
+    st = syn.kube_objects(c)
+    nodes, pods = [Obj(o) for o in st["nodes"]], [Obj(o) for o in st["pods"]]
+    cl = Cluster(None, 1800, 1, "a", "b", "c", "d", "e", "f", 600, "rg", None, "", over_provision=c["over_provision"], dry_run=True)
+    cl.list_nodes, cl.list_pods = (lambda: nodes), (lambda: pods)
+    cl.arm_template, cl.arm_parameters = {}, st["arm_parameters"]
+    calls = []
+    orig_init = agent_pool.AgentPool.__init__
+
+    def pool_init(self, *a, **k):  # AgentPool.max_size is a plain attribute (100 upstream): the benchmark pools are unbounded
+        orig_init(self, *a, **k)
+        self.max_size = int(c["pool_max"][0])
+    agent_pool.AgentPool.__init__ = pool_init
+    prev_engine = snapshot._engine
+    snapshot.set_engine(eng)
+    logging.disable(logging.CRITICAL)
+    try:
+        times = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            ok = cl.loop_logic()
+            times.append(time.perf_counter() - t0)
+            calls.append(ok)
+    finally:
+        logging.disable(logging.NOTSET)
+        agent_pool.AgentPool.__init__ = orig_init
+        snapshot._engine = prev_engine
+    best = min(times[1:])
+    return {"seconds_per_tick": best, "pods": len(pods), "nodes": len(nodes), "returned": bool(calls[-1]),
+            "pods_per_s": len(pods) / best,
+            "what": "Cluster.loop_logic(), dry run, on kube-style dicts of the c2 snapshot (best of %d after one warm-up): "
+                    "KubePod / KubeNode construction, flattening, GPU tick, decisions mapped back" % reps}
+
+
 def run_single(args):
     import torch
     from kubernetes_acs_engine_autoscaler_b200 import build as acs_build
@@ -472,7 +532,7 @@ def run_single(args):
                      "note": "achieved = SURVEY 8(d) algorithmic bytes (8*D per decision) / kernel time; node and bin "
                              "rows are held on chip, so real DRAM traffic (`traffic`, ncu) is far below it: the "
                              "kernel is not HBM-bound, `physical` names what does bound it",
-                     "physical": physical_roofline(k_dec / (k_ms * 1e-3), nw, clk.get("sm_mhz"))},
+                     "physical": physical_roofline(k_dec / (k_ms * 1e-3), nw, clk.get("sm_mhz"), k_ms, res["n_to_schedule"])},
         "e2e": {"value": res["decisions"] * args.steps / (host_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(w.h2d),
                 "d2h_bytes_per_step": int(w.d2h), "ms_per_step": host_ms / args.steps,
                 "path": "acsfit_occupancy_host + acsfit_scale_up_host + acsfit_maintain_host on pinned host arrays"},
@@ -486,8 +546,11 @@ def run_single(args):
         try:
             if args.config != "c3":
                 configs["c3"], c3_rate = sub_record_c3(eng, syn, flush, max(1, min(args.steps, 3)), peak)
-                configs["c3"]["roofline"]["physical"] = physical_roofline(c3_rate, 0 if nw == 0 else 1, clk.get("sm_mhz"))
+                configs["c3"]["roofline"]["physical"] = physical_roofline(
+                    c3_rate, 0 if nw == 0 else 1, clk.get("sm_mhz"), configs["c3"]["roofline"]["kernel_ms_per_step"], CONFIGS["c3"][0])
             configs["c5"] = sub_record_c5(eng, syn, flush, peak)
+            if args.config == "c2":
+                line["e2e"]["python_surface"] = python_surface(eng, syn, c)
         except Exception as e:  # a sub-record must never take the headline down
             configs["error"] = "%s: %s" % (type(e).__name__, e)
         line["configs"] = configs

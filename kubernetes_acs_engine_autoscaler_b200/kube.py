@@ -59,6 +59,45 @@ class KubeResource(object):
         return str(self.raw)
 
 
+_RESOURCES_MEMO = {}
+_CREATED_BY_MEMO = {}
+
+
+def _pod_resources(containers):
+    """KubePod.resources (kube.py:41-49): pods:1 + the per-key sum over the containers' requests, accumulated as
+    0.0 + v1 + v2 ... in container order (the order fixes the float64 result).  A cluster's pods come from a few
+    templates, so the result is memoised on the literal request texts; pods with the same requests then SHARE one
+    KubeResource (they are values: nothing in this package mutates one in place), which also lets the snapshot
+    flattening convert each distinct vector once (snapshot.Dims).  Failures are not cached: they raise again."""
+    try:
+        if len(containers) == 1:  # the common case, without building a generator
+            r = containers[0].get('resources')
+            q = r.get('requests') if r else None
+            key = tuple(q.items()) if q else ()
+        else:
+            key = []
+            for c in containers:
+                r = c.get('resources')
+                q = r.get('requests') if r else None
+                key.append(tuple(q.items()) if q else ())
+            key = (len(containers), tuple(key))
+        hit = _RESOURCES_MEMO.get(key)
+    except TypeError:  # unhashable quantity objects: the plain route
+        key, hit = None, None
+    if hit is not None:
+        return hit
+    totals = {}
+    for container in containers:
+        for name, quantity in container.get('resources', {}).get('requests', {}).items():
+            totals[name] = totals.get(name, 0.0) + utils.parse_SI(quantity)
+    res = KubeResource(pods=1, **totals)
+    if key is not None:
+        if len(_RESOURCES_MEMO) > (1 << 16):
+            _RESOURCES_MEMO.clear()
+        _RESOURCES_MEMO[key] = res
+    return res
+
+
 class KubePod(object):
     _DRAIN_GRACE_PERIOD = datetime.timedelta(seconds=60 * 60)
 
@@ -77,23 +116,23 @@ class KubePod(object):
         self.owner = self.labels.get('owner', None)
         self.creation_time = utils.parse_time(meta['creationTimestamp'])
         self.start_time = utils.parse_time(status['startTime']) if 'startTime' in status else None
-        # resources = pods:1 + per-key sum over containers, accumulated as 0.0 + v1 + v2 ... in
-        # container order (kube.py:41-49): the order fixes the float64 result
-        totals = {}
-        for container in spec['containers']:
-            for key, quantity in container.get('resources', {}).get('requests', {}).items():
-                totals[key] = totals.get(key, 0.0) + utils.parse_SI(quantity)
-        self.resources = KubeResource(pods=1, **totals)
+        self.resources = _pod_resources(spec['containers'])
 
     def _created_by(self):
-        """the created-by annotation, decoded (kube.py:51-58 decode it on every call; the text does not change
-        while a tick holds the object, so it is decoded once per text; a malformed annotation raises every time)"""
+        """the created-by annotation, decoded (kube.py:51-58 decode it on every call).  The decoded value is a pure
+        function of the text and only ever read, so it is memoised per distinct text (the pods of one controller
+        share theirs); a malformed annotation is not cached and raises on every call, as upstream."""
         text = self.annotations.get('kubernetes.io/created-by', '{}')
-        cached = self.__dict__.get('_created_by_cache')
-        if cached is None or cached[0] is not text:
-            cached = (text, json.loads(text))
-            self.__dict__['_created_by_cache'] = cached
-        return cached[1]
+        try:
+            return _CREATED_BY_MEMO[text]
+        except (KeyError, TypeError):
+            pass
+        decoded = json.loads(text)
+        if type(text) is str:
+            if len(_CREATED_BY_MEMO) > (1 << 16):
+                _CREATED_BY_MEMO.clear()
+            _CREATED_BY_MEMO[text] = decoded
+        return decoded
 
     def is_mirrored(self):
         daemonset = self._created_by().get('reference', {}).get('kind') == 'DaemonSet'

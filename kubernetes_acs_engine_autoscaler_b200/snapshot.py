@@ -33,12 +33,17 @@ def set_engine(engine):
 
 
 class Dims(object):
-    """column order of one flattening."""
+    """column order of one flattening.  Resource vectors are deduplicated by object identity first: pods of one
+    template share their KubeResource (kube._pod_resources), so 10^5 pods flatten as a few dozen distinct rows
+    plus one fancy-index, not as 10^5 Python dict walks."""
 
     def __init__(self, resources):
         keys = set()
+        seen = set()
         for res in resources:
-            keys.update(res.raw.keys())
+            if id(res) not in seen:
+                seen.add(id(res))
+                keys.update(res.raw.keys())
         self.keys = sorted(keys)
         self.index = {k: i for i, k in enumerate(self.keys)}
         self.D = max(1, len(self.keys))
@@ -46,11 +51,22 @@ class Dims(object):
 
     def rows(self, resources, n=None):
         resources = list(resources)
-        out = np.zeros((len(resources) if n is None else n, self.Dp), dtype=np.float64)
         index = self.index
+        slot, uniq = {}, []
+        inv = np.empty(len(resources), dtype=np.int64)
         for i, res in enumerate(resources):
+            j = slot.get(id(res))
+            if j is None:
+                j = slot[id(res)] = len(uniq)
+                uniq.append(res)
+            inv[i] = j
+        urows = np.zeros((len(uniq), self.Dp), dtype=np.float64)
+        for j, res in enumerate(uniq):
             for key, value in res.raw.items():
-                out[i, index[key]] = value
+                urows[j, index[key]] = value
+        out = np.zeros((len(resources) if n is None else n, self.Dp), dtype=np.float64)
+        if len(resources):
+            out[:len(resources)] = urows[inv]
         return out
 
 
@@ -243,13 +259,32 @@ POD_BUSY, POD_UNDRAINABLE = 1, 2
 NODE_UNSCHEDULABLE = 1
 
 
-def pod_flags(pod):
-    """host-computed booleans of get_node_state (scaler.py:76, :82-83)."""
+def pod_flags(pod, now_by_tz=None):
+    """host-computed booleans of get_node_state (scaler.py:76, :82-83).  `now_by_tz` (a dict) lets a batch read
+    the clock once per time zone instead of once per pod (kube.py:68 reads it per call; within one maintain pass
+    the readings differ by microseconds against a one-hour grace period)."""
     proxy = 'kube-proxy' in pod.name
     flags = 0
     if not pod.is_mirrored() and not proxy:
         flags |= POD_BUSY
-    if not (pod.is_drainable() or proxy):
+    if proxy:
+        return flags
+    if now_by_tz is None:
+        drainable = pod.is_drainable()
+    else:  # is_drainable(), with the clock of the batch (same short-circuit order: replicated, critical, grace)
+        drainable = pod.is_replicated() and not pod.is_critical()
+        if drainable:
+            start = pod.start_time
+            if not start:
+                drainable = False
+            else:
+                tz = start.tzinfo
+                now = now_by_tz.get(id(tz))  # (tzinfo objects need not be hashable: keyed by identity)
+                if now is None:
+                    from . import utils
+                    now = now_by_tz[id(tz)] = utils.now(tz)
+                drainable = not ((now - start) < pod._DRAIN_GRACE_PERIOD)
+    if not drainable:
         flags |= POD_UNDRAINABLE
     return flags
 
@@ -273,7 +308,8 @@ def node_states(nodes, pods_lists, any_pending, idle_threshold):
     req_run = dims.rows(p.resources for p in flat) if flat else np.zeros((0, dims.Dp))
     if (req_run < 0).any() or np.isnan(req_run).any():
         raise ValueError("negative or NaN resource request")
-    flags = np.asarray([pod_flags(p) for p in flat], dtype=np.uint8)
+    clock = {}
+    flags = np.asarray([pod_flags(p, clock) for p in flat], dtype=np.uint8)
     cap, node_type = _node_types(nodes, dims)
     node_flags = np.asarray([NODE_UNSCHEDULABLE if n.unschedulable else 0 for n in nodes], dtype=np.uint8)
     age = np.asarray([node_age_seconds(n) for n in nodes], dtype=np.int64)

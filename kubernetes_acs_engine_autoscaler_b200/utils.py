@@ -82,19 +82,27 @@ def parse_time(text):
     'YYYY-MM-DDTHH:MM:SSZ' form is decoded directly (dateutil spends ~40 us per call on it, which dominates
     ingestion at 10^5 pods); anything else, or any out-of-range field, goes through dateutil itself so the
     result and the errors are the reference's.  The zone object is the one dateutil itself attaches to a 'Z'
-    timestamp on this host (tzlocal() where the local zone is UTC, tzutc() elsewhere), asked once."""
+    timestamp on this host (tzlocal() where the local zone is UTC, tzutc() elsewhere), asked once.
+    Exact `str` inputs are memoised: a pure function of the text, and pods created in one burst share theirs."""
+    if type(text) is str:
+        return _parse_time_text(text)
+    from dateutil.parser import parse
+    return parse(text)
+
+
+@functools.lru_cache(maxsize=1 << 16)
+def _parse_time_text(text):
     global _Z_ZONE
     if _Z_ZONE is None:
         from dateutil.parser import parse
         _Z_ZONE = parse("2000-01-01T00:00:00Z").tzinfo
-    if isinstance(text, str):
-        m = _RFC3339_Z.match(text)
-        if m is not None:
-            try:
-                y, mo, d, h, mi, sec = (int(g) for g in m.groups())
-                return datetime.datetime(y, mo, d, h, mi, sec, tzinfo=_Z_ZONE)
-            except ValueError:
-                pass
+    m = _RFC3339_Z.match(text)
+    if m is not None:
+        try:
+            return datetime.datetime(int(text[0:4]), int(text[5:7]), int(text[8:10]), int(text[11:13]), int(text[14:16]),
+                                     int(text[17:19]), tzinfo=_Z_ZONE)
+        except ValueError:
+            pass
     from dateutil.parser import parse
     return parse(text)
 

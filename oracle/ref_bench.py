@@ -30,91 +30,15 @@ for p in (ROOT, HERE):
 import ref_shim  # noqa: E402
 from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn  # noqa: E402
 
-NOW = datetime.datetime(2026, 9, 21, 12, 0, 0, tzinfo=datetime.timezone.utc)
-CLUSTER_ID = "16334397"
 
 
-def quantity(dim_name, value):
-    """the kube quantity string that utils.parse_SI turns back into `value` (checked)."""
-    if dim_name == "cpu":
-        n = int(round(value * 1000.0))
-        s, back = "%dm" % n, float(n) * 1e-3
-    elif dim_name == "memory":
-        n = int(round(value / float(2 ** 20)))
-        s, back = "%dMi" % n, float(n) * float(2 ** 20)
-    else:
-        n = int(round(value))
-        s, back = "%d" % n, float(n)
-    if back != value:
-        raise ValueError("%r of %s has no exact quantity string" % (value, dim_name))
-    return s
-
-
-def requests_of(row, dim_names):
-    """container `requests` dict of one dense row (the `pods` column is KubePod's own pods=1, kube.py:49)."""
-    return {name: quantity(name, float(v)) for name, v in zip(dim_names, row) if name != "pods" and v != 0.0}
-
-
-def iso(dt):
-    return dt.strftime("%Y-%m-%dT%H:%M:%SZ")
-
-
-def pool_name(t):
-    return "pool%d" % t
-
-
-def node_name(t, i):
-    return "k8s-%s-%s-%d" % (pool_name(t), CLUSTER_ID, i)
-
-
-def kube_state(c):
-    """synthetic cluster dict -> {'nodes': [...], 'pods': [...], 'arm_parameters': {...}} of kube-style dicts.
-    Pod list order: the running pods in CSR order (per node, list order), then the pending pods."""
-    names = c["dim_names"]
-    N, T = c["N"], c["T"]
-    nodes = []
-    for i in range(N):
-        t = int(c["node_type"][i])
-        created = NOW - datetime.timedelta(seconds=int(c["node_age"][i]))
-        spec = {"unschedulable": True} if c["node_flags"][i] & 1 else {}
-        nodes.append({"metadata": {"name": node_name(t, i), "creationTimestamp": iso(created),
-                                   "labels": {"beta.kubernetes.io/instance-type": syn.INSTANCE_TYPES[t][0],
-                                              "failure-domain.beta.kubernetes.io/region": "southcentralus",
-                                              "kubernetes.io/hostname": node_name(t, i)}},
-                      "spec": spec})
-    pods = []
-    old = iso(NOW - datetime.timedelta(hours=5))
-    row_ptr, run_idx = c["row_ptr"], c["run_idx"]
-    for i in range(N):
-        t = int(c["node_type"][i])
-        for k in range(int(row_ptr[i]), int(row_ptr[i + 1])):
-            j = int(run_idx[k])
-            f = int(c["flags_run"][j])
-            md = {"name": "run-%d" % j, "namespace": "default", "uid": "run-%d" % j, "creationTimestamp": old}
-            # flag bits (include/acsfit.h): 1 = busy (not mirrored), 2 = undrainable; kube.py:51-71
-            if f == 0:    # DaemonSet pod: mirrored (not busy) and replicated (drainable)
-                md["annotations"] = {"kubernetes.io/created-by": json.dumps(
-                    {"kind": "SerializedReference", "reference": {"kind": "DaemonSet", "name": "ds"}})}
-            elif f == 2:  # static (mirror) pod: not busy, but not drainable either
-                md["annotations"] = {"kubernetes.io/config.mirror": "x"}
-            elif f == 1:  # ReplicaSet pod: busy and drainable
-                md["annotations"] = {"kubernetes.io/created-by": json.dumps(
-                    {"kind": "SerializedReference", "reference": {"kind": "ReplicaSet", "name": "rs"}})}
-            # f == 3: a bare pod, busy and undrainable -- no annotation
-            pods.append({"metadata": md,
-                         "spec": {"nodeName": node_name(t, i),
-                                  "containers": [{"name": "c", "resources": {"requests": requests_of(c["req_run"][j], names)}}]},
-                         "status": {"phase": "Running", "startTime": old}})
-    for p in range(c["P"]):
-        pods.append({"metadata": {"name": "pend-%d" % p, "namespace": "default", "uid": "pend-%d" % p,
-                                  "creationTimestamp": old},
-                     "spec": {"containers": [{"name": "c", "resources": {"requests": requests_of(c["req"][p], names)}}]},
-                     "status": {"phase": "Pending"}})
-    arm = {"masterVMSize": {"value": "Standard_D2_v2"}}
-    for t in range(T):
-        arm[pool_name(t) + "Count"] = {"value": 1}
-        arm[pool_name(t) + "VMSize"] = {"value": syn.INSTANCE_TYPES[t][0]}
-    return {"nodes": nodes, "pods": pods, "arm_parameters": arm}
+# the kube-API style view of a synthetic snapshot lives with the generator (product side, also used by bench.py)
+quantity = syn.quantity
+requests_of = syn.requests_of
+pool_name = syn.pool_name
+node_name = syn.node_name
+kube_state = syn.kube_objects
+NOW = syn.NOW
 
 
 def capacity_file(c, directory):
