@@ -106,7 +106,8 @@ ACSFIT_API acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx);
  *   ACSFIT_RANKS=0          never use the packed-rank scan (float64 compares instead; same results) */
 ACSFIT_API acsfit_status acsfit_ctx_configure(acsfit_ctx *ctx, int min_stages, int watchdog_ms);
 /* the same developer knobs by name, after ctx creation: "ranks" (0: float64 compare scan, 1: packed-rank scan when
- * the tick's request table allows it -- the default), "prune", "overlap", "min_stages", "inject_chain_timeout" (test hook), "cluster_blocks" (cluster
+ * the tick's request table allows it -- the default), "stream" (1: the barrier-free streaming form of the pipeline
+ * kernel, csrc/acsfit_stream_ff.cuh, where it applies; env ACSFIT_STREAM), "prune", "overlap", "min_stages", "inject_chain_timeout" (test hook), "cluster_blocks" (cluster
  * mode: cut the pod list of the node pass into this many blocks; 0 = automatic).  None changes a result. */
 ACSFIT_API acsfit_status acsfit_ctx_set_knob(acsfit_ctx *ctx, const char *name, int value);
 /* when enabled, the first-fit / bin-pack pipeline launches are bracketed with CUDA events on the

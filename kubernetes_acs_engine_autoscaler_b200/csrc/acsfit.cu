@@ -19,6 +19,7 @@
 #include "acsfit_kernels.cuh"
 #include "acsfit_rank.cuh"
 #include "acsfit_stream.cuh"
+#include "acsfit_stream_ff.cuh"
 
 using namespace acsfit;
 
@@ -32,6 +33,7 @@ struct acsfit_ctx {
     int watchdog_ms = 20000;
     std::map<std::tuple<int, int, int, int, int>, int> resident_cache;  // (D, bins, prune, rank words, Tn) -> stage CTAs the GPU holds
     int prune = -1;           // -1: automatic (node passes that run in waves), 0 / 1: forced (ACSFIT_PRUNE)
+    int use_stream = 0;       // barrier-free streaming form of the pipeline kernel (acsfit_stream_ff.cuh; ACSFIT_STREAM / knob "stream")
     int use_ranks = 1;        // packed-rank scan when the tick's distinct request values allow it (ACSFIT_RANKS=0: never)
     RankLayout rk;            // rank tables of the current API call (rk.nw == 0: float64 scan)
     // cluster mode (one cluster on `world` GPUs; see include/acsfit.h)
@@ -762,6 +764,7 @@ extern "C" acsfit_status acsfit_ctx_create(int device, acsfit_ctx **out_ctx)
     if (const char *env = getenv("ACSFIT_OVERLAP")) ctx->overlap = atoi(env) != 0;
     if (const char *env = getenv("ACSFIT_PRUNE")) ctx->prune = atoi(env);
     if (const char *env = getenv("ACSFIT_RANKS")) ctx->use_ranks = atoi(env) != 0;
+    if (const char *env = getenv("ACSFIT_STREAM")) ctx->use_stream = atoi(env) != 0;
     memset(&ctx->rk, 0, sizeof ctx->rk);
     if (const char *env = getenv("ACSFIT_MIN_STAGES")) ctx->min_stages = std::max(0, atoi(env));
     if (const char *env = getenv("ACSFIT_STREAM_BYTES")) g_stream_bytes = atoi(env);
@@ -804,6 +807,7 @@ extern "C" acsfit_status acsfit_ctx_set_knob(acsfit_ctx *ctx, const char *name, 
 {
     if (!ctx || !name) return ACSFIT_E_INVALID;
     if (!strcmp(name, "ranks")) ctx->use_ranks = value != 0;
+    else if (!strcmp(name, "stream")) ctx->use_stream = value != 0;
     else if (!strcmp(name, "prune")) ctx->prune = value;
     else if (!strcmp(name, "overlap")) ctx->overlap = value != 0;
     else if (!strcmp(name, "min_stages")) ctx->min_stages = std::max(0, value);
@@ -996,7 +1000,8 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
     const int want = ctx->min_stages > 0 ? ctx->min_stages : ctx->num_sms;  // one stage per SM measured best
     const int K = nodes_per_thread(D, ctx->rk.nw);
     int NS = max_stage_nodes(D, bins) / K;
-    while (NS > 1 && (n_nodes + (int64_t)NS * K - 1) / ((int64_t)NS * K) < want) NS >>= 1;
+    const int ns_min = (ctx->use_stream && ctx->rk.nw > 0 && D <= 8) ? std::max(1, 32 / K) : 1;  // streaming form: stages of >= 32 nodes
+    while (NS > ns_min && (n_nodes + (int64_t)NS * K - 1) / ((int64_t)NS * K) < want) NS >>= 1;
     StagePlan p;
     p.NS = NS;
     p.Tn = NS * K;
@@ -1007,9 +1012,41 @@ static StagePlan plan_stages(const acsfit_ctx *ctx, int64_t n_nodes, int max_sta
     return p;
 }
 
+static bool stream_form_ok(const acsfit_ctx *ctx, int D, int nw, int Tn)
+{
+    return ctx->use_stream && nw > 0 && D <= 8 && Tn >= 32 && Tn % 32 == 0;
+}
+
+template <int D, bool BINS, int RW>
+static acsfit_status launch_stream(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
+{
+    const size_t smem = StreamSmem<D, BINS, RW>::bytes(pp.Tn);
+    auto kern = firstfit_stream_kernel<D, BINS, RW>;
+    if (resident) {
+        const auto key = std::make_tuple(D, (int)BINS, 2 /*streaming form*/, RW, pp.Tn);
+        auto it = ctx->resident_cache.find(key);
+        if (it == ctx->resident_cache.end()) {
+            int per_sm = 0;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+            it = ctx->resident_cache.emplace(key, per_sm * ctx->num_sms).first;
+        }
+        *resident = it->second;
+        return ACSFIT_OK;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<stages, 256, smem, st>>>(pp);
+    ++ctx->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ACSFIT_OK;
+}
+
 template <int D, bool BINS, bool PRUNE, int RW>
 static acsfit_status launch_pipeline_w(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
 {
+    if constexpr (RW > 0 && D <= 8 && !PRUNE) {
+        if (stream_form_ok(ctx, D, RW, pp.Tn)) return launch_stream<D, BINS, RW>(ctx, pp, stages, st, resident);
+    }
     constexpr int NT = stage_threads(D, BINS);
     size_t smem = PipelineSmem<D, BINS, NT, PRUNE, RW>::bytes(pp.Tn);
     if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
@@ -1063,6 +1100,7 @@ static acsfit_status launch_pipeline_t(acsfit_ctx *ctx, const PipelineParams &pp
         // placement chain and runs the plain instantiation (measured: c3 nodes pass 143 -> 128 ms with pruning,
         // c2 tick 10.75 -> 10.93 ms).  ACSFIT_PRUNE=0/1 forces either.
         int prune = ctx->prune;
+        if (prune != 1 && stream_form_ok(ctx, D, pp.rk.nw, pp.Tn)) prune = 0;  // the streaming form has no pruning variant
         if (prune < 0) {
             int resident = 0;
             TRY((launch_pipeline_v<D, BINS, false>(ctx, pp, stages, st, &resident)));

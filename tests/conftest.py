@@ -21,10 +21,11 @@ def oracle_mod():
     return oracle
 
 
-@pytest.fixture(scope="session", params=["ranks", "f64"])
+@pytest.fixture(scope="session", params=["ranks", "f64", "stream"])
 def engine(request):
-    """the product engine on cuda:0; GPU tests only.  Every test runs with both forms of the candidate scan:
-    packed-rank integer compares (the default) and float64 compares (the fallback for huge request tables)."""
+    """the product engine on cuda:0; GPU tests only.  Every test runs with both forms of the candidate scan --
+    packed-rank integer compares (the default) and float64 compares (the fallback for huge request tables) -- and
+    with the barrier-free streaming form of the pipeline kernel (csrc/acsfit_stream_ff.cuh)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -32,6 +33,7 @@ def engine(request):
     acs_build.build()
     from kubernetes_acs_engine_autoscaler_b200.engine import Engine
     eng = Engine(0, watchdog_ms=15000)
-    eng.set_knob("ranks", 1 if request.param == "ranks" else 0)
+    eng.set_knob("ranks", 0 if request.param == "f64" else 1)
+    eng.set_knob("stream", 1 if request.param == "stream" else 0)
     yield eng
     eng.close()

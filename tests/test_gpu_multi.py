@@ -26,6 +26,8 @@ CASES = [
     (20000, 3000, 8, 8, 11, {"cluster_blocks": 3}),     # pod blocks forced (the multi-wave schedule)
     (20000, 3000, 4, 1, 12, {"ranks": 0}),               # float64 scan form
     (60000, 6000, 4, 2, 4242, {}),
+    (20000, 3000, 8, 8, 13, {"stream": 1}),                # barrier-free streaming form of the pipeline kernel
+    (60000, 6000, 4, 2, 4243, {"stream": 1, "cluster_blocks": 2}),
 ]
 
 
@@ -53,6 +55,7 @@ def _worker(rank, world, port, out_dir, backend, devices):
         used0 = syn.initial_used(c)
         for e in (solo, eng):
             e.set_knob("ranks", knobs.get("ranks", 1))
+            e.set_knob("stream", knobs.get("stream", 0))
         eng.set_knob("cluster_blocks", knobs.get("cluster_blocks", 0))
         args = (c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"], c["pool_ignored"], c["over_provision"])
         u1, u2 = solo.dev(used0, f64), eng.dev(used0, f64)
