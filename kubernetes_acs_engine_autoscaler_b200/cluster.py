@@ -140,6 +140,10 @@ class Cluster(object):
         return kube_node
 
     def loop_logic(self):
+        with utils.gc_paused():  # a tick builds 10^5 small objects at once: generational GC passes would double its time
+            return self._loop_logic()
+
+    def _loop_logic(self):
         pykube_nodes = self.list_nodes()
         if not pykube_nodes:
             logger.warning('Failed to list nodes. Please check kube configuration. Terminating scale loop.')

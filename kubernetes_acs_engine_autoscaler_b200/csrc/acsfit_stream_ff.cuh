@@ -395,38 +395,61 @@ firstfit_stream_kernel(const PipelineParams p)
                     __syncwarp();
                     double r[D];
                     load_row<D>(r, brow);
-                    unsigned took = 0, mymask = 0;
-                    const unsigned me = 1u << lane, le = (me << 1) - 1u;
+                    unsigned took = 0;    // bit k: dense entry k of the batch was placed by this warp
+                    unsigned mymask = 0;  // bit k: ... by THIS lane's node
+                    const unsigned me = 1u << lane, le = (me << 1) - 1u;  // this lane's bit, and all bits up to it
+                    // The placement chain.  Entry k's test needs the state left by entry k-1, which is only known once
+                    // the vote of entry k-1 has named its taker.  Instead of waiting for it, both outcomes are computed
+                    // while that vote is in flight: fit_keep = "entry k fits this node as it is", fit_took = "... after
+                    // this node took entry k-1" (the same float64 expressions, same rounding), and the vote's answer
+                    // merely selects one.  What stays on the vote-to-vote path is a predicate select and a mask
+                    // compare; the float64 adds and compares run beside it.
+                    auto fits = [&](const double (&st)[D], const double (&row)[D]) {
+                        bool ok = true, ok2 = true;  // two independent and-chains over the dimensions
+#pragma unroll
+                        for (int d = 0; d < D / 2; ++d) {
+                            if (BINS) ok = ok & (row[d] <= st[d]);   // == (st - row >= 0) for finite values (scaler.py:139)
+                            else ok = ok & (__dsub_rn(C[d], __dadd_rn(st[d], row[d])) >= 0.0);  // kube.py:175
+                        }
+#pragma unroll
+                        for (int d = D / 2; d < D; ++d) {
+                            if (BINS) ok2 = ok2 & (row[d] <= st[d]);
+                            else ok2 = ok2 & (__dsub_rn(C[d], __dadd_rn(st[d], row[d])) >= 0.0);
+                        }
+                        return ok & ok2;
+                    };
+                    double Sm[D];  // the state this node would have after taking the previous entry
+#pragma unroll
+                    for (int d = 0; d < D; ++d) Sm[d] = S[d];
+                    bool prev_mine = false;
+                    bool fit_keep = fits(S, r), fit_took = fit_keep;
                     for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
                     for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
                         double r_next[D];
                         load_row<D>(r_next, brow + (size_t)(k + 1) * D);
-                        bool ok = true, ok2 = true;
+                        const bool ok = prev_mine ? fit_took : fit_keep;
+                        if (prev_mine) {
 #pragma unroll
-                        for (int d = 0; d < D / 2; ++d) {
-                            if (BINS) ok = ok & (r[d] <= S[d]);   // == (S - r >= 0) for finite values (scaler.py:139)
-                            else ok = ok & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);  // kube.py:175
+                            for (int d = 0; d < D; ++d) S[d] = Sm[d];
                         }
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                        // beside the vote: the state after taking THIS entry, and the next entry's test either way
 #pragma unroll
-                        for (int d = D / 2; d < D; ++d) {
-                            if (BINS) ok2 = ok2 & (r[d] <= S[d]);
-                            else ok2 = ok2 & (__dsub_rn(C[d], __dadd_rn(S[d], r[d])) >= 0.0);
-                        }
-                        const bool any = __any_sync(0xFFFFFFFFu, ok & ok2);
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok & ok2);
-                        if (any) {
-                            if ((m & le) == me) {  // the first fitting node of the warp takes the pod
-#pragma unroll
-                                for (int d = 0; d < D; ++d)
-                                    S[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
-                                                : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
-                                mymask |= 1u << k;
-                            }
-                            took |= 1u << k;
-                        }
+                        for (int d = 0; d < D; ++d)
+                            Sm[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
+                                         : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
+                        fit_keep = fits(S, r_next);
+                        fit_took = fits(Sm, r_next);
+                        prev_mine = (m & le) == me;  // the first fitting node of the warp takes the pod
+                        if (prev_mine) mymask |= 1u << k;
+                        if (m) took |= 1u << k;
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
+                    }
+                    if (prev_mine) {  // the last entry's taker
+#pragma unroll
+                        for (int d = 0; d < D; ++d) S[d] = Sm[d];
                     }
                     for (unsigned t = mymask; t; t &= t - 1) fnd[__ffs(t) - 1] = (unsigned char)lane;
                     if (mymask) state_dirty = true;

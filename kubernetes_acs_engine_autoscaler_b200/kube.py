@@ -61,6 +61,17 @@ class KubeResource(object):
 
 _RESOURCES_MEMO = {}
 _CREATED_BY_MEMO = {}
+_TIME_MEMO = {}
+_MISSING = object()
+
+
+def _remember_time(text):
+    value = utils.parse_time(text)  # raises like the reference for a malformed timestamp (not cached)
+    if type(text) is str:
+        if len(_TIME_MEMO) > (1 << 16):
+            _TIME_MEMO.clear()
+        _TIME_MEMO[text] = value
+    return value
 
 
 def _pod_resources(containers):
@@ -111,11 +122,19 @@ class KubePod(object):
         self.status = status['phase']
         self.uid = meta['uid']
         self.selectors = spec.get('nodeSelector', {})
-        self.labels = meta.get('labels', {})
+        self.labels = labels = meta.get('labels', {})
         self.annotations = meta.get('annotations', {})
-        self.owner = self.labels.get('owner', None)
-        self.creation_time = utils.parse_time(meta['creationTimestamp'])
-        self.start_time = utils.parse_time(status['startTime']) if 'startTime' in status else None
+        self.owner = labels.get('owner', None)
+        # (timestamps: memoised per text, utils.parse_time; the memo is consulted directly on this hot path)
+        text = meta['creationTimestamp']
+        cached = _TIME_MEMO.get(text) if type(text) is str else None
+        self.creation_time = cached if cached is not None else _remember_time(text)
+        text = status.get('startTime', _MISSING)
+        if text is _MISSING:
+            self.start_time = None
+        else:
+            cached = _TIME_MEMO.get(text) if type(text) is str else None
+            self.start_time = cached if cached is not None else _remember_time(text)
         self.resources = _pod_resources(spec['containers'])
 
     def _created_by(self):

@@ -4,7 +4,9 @@ These define the float64 BIT PATTERNS every later stage consumes, so they follow
 exactly (autoscaler/utils.py:6-74): a quantity is `float(digits) * multiplier`, never
 `digits / 1000`.  tests/golden/parse_vectors.json pins them against the reference.
 """
+import contextlib
 import datetime
+import gc
 import functools
 import re
 
@@ -105,6 +107,19 @@ def _parse_time_text(text):
             pass
     from dateutil.parser import parse
     return parse(text)
+
+
+@contextlib.contextmanager
+def gc_paused():
+    """suspend the cyclic garbage collector while a tick builds its objects in bulk (nothing in a tick creates
+    reference cycles that must be reclaimed mid-tick); restored on exit, whatever happens."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 # injectable clock: the reference calls datetime.datetime.now(tz) inline (scaler.py:78, kube.py:68);
