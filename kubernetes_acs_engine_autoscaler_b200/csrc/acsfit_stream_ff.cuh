@@ -418,6 +418,34 @@ firstfit_stream_kernel(const PipelineParams p)
                         }
                         return ok & ok2;
                     };
+                    // (twice the float64 work per entry: it pays where a test is one compare per dimension -- bins -- or the
+                    // row is short; the D = 8 node test, 24 float64 instructions per entry, is issue-bound and keeps
+                    // the plain form: measured c3 nodes 98 -> 106 ms with it, bins 102 -> 84 ms)
+                    constexpr bool kSpeculate = BINS || D <= 4;
+                    if constexpr (!kSpeculate) {
+                        for (int k0 = 0; k0 < n_poss; k0 += 4)
+#pragma unroll
+                        for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
+                            double r_next[D];
+                            load_row<D>(r_next, brow + (size_t)(k + 1) * D);
+                            const bool ok = fits(S, r);
+                            // two votes issued back to back: the predicate one steers the (uniform) branch without an
+                            // integer compare on the chain, the ballot names the first fitting node
+                            const bool any = __any_sync(0xFFFFFFFFu, ok);
+                            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                            if (any) {
+                                if ((m & le) == me) {  // the first fitting node of the warp takes the pod
+#pragma unroll
+                                    for (int d = 0; d < D; ++d)
+                                        S[d] = BINS ? __dsub_rn(S[d], r[d]) : __dadd_rn(S[d], r[d]);  // scaler.py:140 / kube.py:171
+                                    mymask |= 1u << k;
+                                }
+                                took |= 1u << k;
+                            }
+#pragma unroll
+                            for (int d = 0; d < D; ++d) r[d] = r_next[d];
+                        }
+                    } else {
                     double Sm[D];  // the state this node would have after taking the previous entry
 #pragma unroll
                     for (int d = 0; d < D; ++d) Sm[d] = S[d];
@@ -451,6 +479,7 @@ firstfit_stream_kernel(const PipelineParams p)
 #pragma unroll
                         for (int d = 0; d < D; ++d) S[d] = Sm[d];
                     }
+                    }  // kSpeculate
                     for (unsigned t = mymask; t; t &= t - 1) fnd[__ffs(t) - 1] = (unsigned char)lane;
                     if (mymask) state_dirty = true;
                     __syncwarp();
