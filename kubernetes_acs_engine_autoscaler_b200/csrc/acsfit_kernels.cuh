@@ -211,7 +211,7 @@ __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, in
 }
 
 template <int D, bool BINS, int NT, bool PRUNE, int RW>
-__global__ void __launch_bounds__(NT, D <= 4 ? 2 : 1)  // D <= 4: two stage CTAs per SM (needed to chain nodes -> bins)
+__global__ void __launch_bounds__(NT)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
     constexpr int K = nodes_per_thread(D, RW);  // RW: 32-bit words of a packed-rank row, 0 = float64 scan
@@ -761,10 +761,11 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         }
                         return ok & ok2;
                     };
-                    // (twice the float64 work per entry: it pays where a test is one compare per dimension -- bins -- or the
-                    // row is short; the D = 8 node test, 24 float64 instructions per entry, is issue-bound and keeps
-                    // the plain form: measured c3 nodes 98 -> 106 ms with it, bins 102 -> 84 ms)
-                    constexpr bool kSpeculate = BINS || D <= 4;
+                    // Measured (profiles/r02_summary.md): bins at D = 8 102 -> 84 ms (c3).  Not used where it loses: the D = 8
+                    // node test is 24 float64 instructions per entry and issue-bound (c3 nodes 98 -> 106 ms with it); at
+                    // D <= 4 the extra registers (122 -> 148) cost the second stage CTA per SM, and with it the
+                    // nodes -> bins chaining of the c2 tick (10.7 -> 10.9 ms; capped at 128 registers: 11.6 ms).
+                    constexpr bool kSpeculate = BINS && D >= 8;
                     if constexpr (!kSpeculate) {
                         for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll

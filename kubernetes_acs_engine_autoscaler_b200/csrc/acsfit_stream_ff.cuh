@@ -418,10 +418,11 @@ firstfit_stream_kernel(const PipelineParams p)
                         }
                         return ok & ok2;
                     };
-                    // (twice the float64 work per entry: it pays where a test is one compare per dimension -- bins -- or the
-                    // row is short; the D = 8 node test, 24 float64 instructions per entry, is issue-bound and keeps
-                    // the plain form: measured c3 nodes 98 -> 106 ms with it, bins 102 -> 84 ms)
-                    constexpr bool kSpeculate = BINS || D <= 4;
+                    // Measured (profiles/r02_summary.md): bins at D = 8 102 -> 84 ms (c3).  Not used where it loses: the D = 8
+                    // node test is 24 float64 instructions per entry and issue-bound (c3 nodes 98 -> 106 ms with it); at
+                    // D <= 4 the extra registers (122 -> 148) cost the second stage CTA per SM, and with it the
+                    // nodes -> bins chaining of the c2 tick (10.7 -> 10.9 ms; capped at 128 registers: 11.6 ms).
+                    constexpr bool kSpeculate = BINS && D >= 8;
                     if constexpr (!kSpeculate) {
                         for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
