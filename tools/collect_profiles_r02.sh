@@ -11,6 +11,7 @@ ncu -i gpurun_out/r02_pipeline_c2.ncu-rep --page raw --csv > gpurun_out/r02_pipe
 ncu --set full --clock-control none -k regex:firstfit_pipeline -s 7 -c 7 \
     -o gpurun_out/r02_pipeline_c3 python bench.py --config c3 --steps 1 --warmup 1 --no-cpu-baseline --no-sub > gpurun_out/r02_full_c3.log 2>&1
 ncu -i gpurun_out/r02_pipeline_c3.ncu-rep --page raw --csv > gpurun_out/r02_pipeline_c3_raw.csv 2>/dev/null
+rm -f gpurun_out/r02_pipeline_c3.ncu-rep   # (41 MB: the raw CSV export is what travels back; gpurun merges at most 64 MiB)
 for D in 4 8; do
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:node_stream -c 10 \
       --csv --log-file gpurun_out/r02_idle_D${D}.csv python tools/perf_idle.py --D $D --T $((D==4?1:8)) > gpurun_out/r02_idle_D${D}.log 2>&1
