@@ -75,7 +75,7 @@ class ClockSampler(object):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.25)
 
     def __enter__(self):
         self._thread.start()
@@ -325,6 +325,9 @@ class Workload(object):
         return ms / reps, dec / reps, byt / reps
 
 
+LAST_STEP_MS = []
+
+
 def timed(step_fn, steps, warmup, flush, barrier, launch_count):
     import torch
     for _ in range(warmup):
@@ -340,7 +343,9 @@ def timed(step_fn, steps, warmup, flush, barrier, launch_count):
         res = step_fn()
         b.record()
     barrier()
-    return res, sum(a.elapsed_time(b) for a, b in ev), launch_count() - l0
+    global LAST_STEP_MS
+    LAST_STEP_MS = [a.elapsed_time(b) for a, b in ev]
+    return res, sum(LAST_STEP_MS), launch_count() - l0
 
 
 INT_LANE_OPS_PER_CLK_SM = 77.0  # measured: tools/ubench6.cu, profiles/r02b_ubench6.txt (IADD + LOP3 mix, all SMs busy)
@@ -506,6 +511,7 @@ def run_single(args):
     peak, peak_src = load_peaks()
     with ClockSampler(0) as clocks:
         res, dev_ms, launches = timed(w.step_device, args.steps, args.warmup, flush, nb, lambda: eng.launch_count)
+        step_ms = sorted(LAST_STEP_MS)
         res_h, host_ms, _ = timed(w.step_host, args.steps, max(1, args.warmup // 2), flush, nb, lambda: eng.launch_count)
     assert res_h["decisions"] == res["decisions"]
     k_ms, k_dec, k_bytes = w.pipeline_leg(flush, max(1, min(args.steps, 5)))
@@ -518,7 +524,8 @@ def run_single(args):
     value = res["decisions"] * args.steps / (dev_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "ms_per_step_spread": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, P, N, D, T, 1), "seed": SEED,
                    "decisions_per_step": int(res["decisions"]), "pods_to_schedule": res["n_to_schedule"],

@@ -4,6 +4,7 @@ The packing / classification arithmetic runs in libacsfit.so (first-fit pipeline
 idle scan); this class keeps the reference's surface, log lines and error behaviour.
 """
 import logging
+import os
 
 import numpy as np
 
@@ -40,6 +41,12 @@ LOG_DETAIL_LIMIT = 20000
 class Scaler(object):
     # a node is under-utilised when its busy pods use <= 30 % of every capacity dimension
     UTIL_THRESHOLD = 0.3
+    # What happens when some pending pods cannot be accounted for (a pool at max_size, duplicate uids).  The
+    # reference evaluates an undefined name there (scaler.py:181) and therefore RAISES before scale_pools: one
+    # saturated pool suppresses the scale-up of every other pool for the tick.  True (default) reproduces that, as
+    # the recorded reference ticks require; False is the behaviour the reference evidently meant -- tell the
+    # notifier, then still scale the pools that can grow.  ($ACSFIT_SCALE_WHEN_INSUFFICIENT=1 selects False.)
+    REFERENCE_RAISE_ON_INSUFFICIENT = os.environ.get('ACSFIT_SCALE_WHEN_INSUFFICIENT', '0') in ('', '0')
 
     def __init__(self, resource_group, nodes, over_provision, spare_count, idle_threshold, dry_run,
                  deployments, notifier):
@@ -98,11 +105,15 @@ class Scaler(object):
 
         if unaccounted:
             logger.warning('Failed to scale sufficiently.')
-            # the reference evaluates `self.notifier.notify_failed_to_scale(selectors_hash, pods)` here,
-            # where `selectors_hash` is an undefined name (scaler.py:181): AttributeError when the
-            # notifier lacks the method, NameError otherwise -- and scale_pools is never reached.
-            self.notifier.notify_failed_to_scale
-            raise NameError("name 'selectors_hash' is not defined")
+            if self.REFERENCE_RAISE_ON_INSUFFICIENT:
+                # the reference evaluates `self.notifier.notify_failed_to_scale(selectors_hash, pods)` here,
+                # where `selectors_hash` is an undefined name (scaler.py:181): AttributeError when the
+                # notifier lacks the method, NameError otherwise -- and scale_pools is never reached.
+                self.notifier.notify_failed_to_scale
+                raise NameError("name 'selectors_hash' is not defined")
+            if self.notifier:
+                left = [p for p, t in zip(unique, acc.tolist()) if t < 0]
+                self.notifier.notify_failed_to_scale({}, left)
         self.scale_pools(new_pool_sizes)
         if self.notifier:
             self.notifier.notify_scale(new_pool_sizes, pods, current_pool_sizes)

@@ -88,3 +88,33 @@ def test_notifier_messages_and_aggregation():
     quiet.notify_drained_node("node-1", pods[:2])
     n2 = nt.Notifier(hook="h", post=lambda url, json=None: (_ for _ in ()).throw(RuntimeError("down")))
     n2.notify_drained_node("node-1", pods[:2])    # a failing chat hook never fails the tick
+
+
+def test_insufficient_scale_up_can_still_scale_the_other_pools(host):
+    """ADVICE (round 1): the reference's undefined name at scaler.py:181 makes a saturated pool suppress every
+    scale-up of the tick.  Default stays bug-compatible (the recorded ticks pin it); the opt-out notifies and scales."""
+    from kubernetes_acs_engine_autoscaler_b200 import capacity
+    from kubernetes_acs_engine_autoscaler_b200.engine_scaler import EngineScaler
+    from kubernetes_acs_engine_autoscaler_b200.kube import KubeNode, KubePod
+    j = []
+    node = KubeNode(gu.FakeKubeObject(_node(0), j, "node"))
+    node.capacity = capacity.get_capacity_for_instance_type(node.instance_type)
+    pods = [KubePod(gu.FakeKubeObject(_pod(i), j, "pod")) for i in range(6)]
+    params = {"agentpool1VMSize": {"value": "Standard_D2_v2"}, "masterVMSize": {"value": "Standard_D2_v2"}}
+    failed = []
+    notifier = types.SimpleNamespace(notify_failed_to_scale=lambda sel, left: failed.append([p.name for p in left]),
+                                     notify_scale=lambda *a: None)
+
+    def scaler():
+        s = EngineScaler("rg", [node], 0, 1, 1800, True, None, {}, dict(params), "", notifier)
+        s.agent_pools[0].max_size = 3          # room for two more instances: four of the six pods stay unaccounted
+        return s
+    s = scaler()
+    with pytest.raises(NameError):             # bug-compatible default: raises before scale_pools
+        s.fulfill_pending(pods)
+    s = scaler()
+    s.REFERENCE_RAISE_ON_INSUFFICIENT = False
+    calls = []
+    s.scale_pools = lambda sizes: calls.append(dict(sizes))
+    s.fulfill_pending(pods)
+    assert calls == [{"agentpool1": 3}] and failed == [["p2", "p3", "p4", "p5"]]
