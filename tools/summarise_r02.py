@@ -99,7 +99,7 @@ traffic["what"] = ("dram__bytes_read.sum + dram__bytes_write.sum (ncu): pipeline
 with open(os.path.join(dst, "r02_traffic.json"), "w") as f:
     json.dump(traffic, f, indent=1)
 for name in ("r02_bench.json", "r02_bench_reference.json", "r02_gpu.csv", "r02_scale_n4.json", "r02_scale_n8.json",
-             "r02_sass_ublkcp_count.txt", "r02b_ubench6.txt", "r02c_bench_n2.json"):
+             "r02_sass_ublkcp_count.txt", "r02b_ubench6.txt", "r02_scale_n2.json"):
     p = os.path.join(src, name)
     if os.path.exists(p):
         shutil.copy(p, os.path.join(dst, name))
