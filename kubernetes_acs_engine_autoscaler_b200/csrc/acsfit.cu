@@ -786,6 +786,10 @@ extern "C" acsfit_status acsfit_ctx_destroy(acsfit_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->hbuf) cudaFree(ctx->hbuf);
+    for (int r = 0; r < ACSFIT_MAX_RANKS; ++r)  // cluster mode: unmap the peers' exchange regions, free our own
+        if (ctx->peer[r] && ctx->peer[r] != ctx->xbase) cudaIpcCloseMemHandle(ctx->peer[r]);
+    if (ctx->xbase) cudaFree(ctx->xbase);
+    if (ctx->prof_dev) cudaFree(ctx->prof_dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
