@@ -29,6 +29,31 @@ def test_c2_full_tick_matches_oracle(engine, oracle_mod):
     assert o["decisions"] > 1.5e9  # the configuration the metric is quoted on
 
 
+def test_c3_shaped_tick_matches_oracle_exactly(engine, oracle_mod, request):
+    """BASELINE config 3's SHAPE (8 dims, 8 pools, multi-wave node pass, several bin passes and pools) at half its
+    size -- 500 k pods x 50 k nodes, about 30 G reference decisions -- compared EXACTLY with the plain-C oracle (which
+    needs about a minute for it; run once, for the default engine mode only)."""
+    if "ranks" not in request.node.callspec.id:
+        pytest.skip("one engine mode is enough for the one-minute oracle run (the other modes run every smaller case)")
+    c = syn.make_cluster(500000, 50000, 8, 8, seed=20260925)
+    used0 = syn.initial_used(c)
+    used_o = used0.copy()
+    o = oracle_scale_up(oracle_mod, c, used_o)
+    f64, i32 = torch.float64, torch.int32
+    d_used = engine.dev(used0, f64)
+    g = engine.scale_up(engine.dev(c["req"], f64), c["unit_all"], c["unit_ordered"], c["pool_actual"], c["pool_max"],
+                        c["pool_ignored"], c["over_provision"], engine.dev(c["cap_type"], f64),
+                        engine.dev(c["node_type"], i32), d_used)
+    for k in ("feasible", "placed", "acc_pool"):
+        np.testing.assert_array_equal(to_np(g[k]), o[k], err_msg=k)
+    for k in ("new_size", "units_needed", "bins_opened"):
+        np.testing.assert_array_equal(g[k], o[k], err_msg=k)
+    for k in ("n_to_schedule", "n_pending", "num_unaccounted", "decisions"):
+        assert g[k] == o[k], k
+    np.testing.assert_array_equal(bits(to_np(d_used)), bits(used_o))
+    assert o["decisions"] > 2e10 and (o["bins_opened"] > 0).sum() >= 3 and o["n_pending"] > 100000
+
+
 def ordered_used(used0, req, placed):
     """used after counting the placed pods in pod order (numpy, host): the reference's count_pod."""
     used = used0.copy()
@@ -109,9 +134,9 @@ def test_c3_fulfill_properties(engine, oracle_mod):
 
 
 def test_c5_idle_scan_matches_oracle(engine, oracle_mod):
-    """BASELINE config 5 shape (scaled to what the oracle does in seconds): 300k nodes, ~3M running pods,
-    8 idle thresholds, then the maintain decisions in both modes; plus the occupancy sums."""
-    c = syn.make_idle_cluster(300000, 8, 8, seed=31)
+    """BASELINE config 5 at its full size: 1 M nodes, ~10 M running pods, 8 idle thresholds (the C oracle needs about a
+    second per kernel for it), then the maintain decisions in both modes; plus the occupancy sums."""
+    c = syn.make_idle_cluster(1000000, 8, 8, seed=31)
     thr = np.array([60, 300, 900, 1800, 3600, 7200, 21600, 86400], dtype=np.int64)
     st_o = oracle_mod.node_states(c["row_ptr"], c["run_idx"], c["req_run"], c["flags_run"], c["cap_type"],
                                   c["node_type"], c["node_flags"], c["node_age"], False, thr)
