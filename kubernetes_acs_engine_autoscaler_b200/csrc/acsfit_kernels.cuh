@@ -155,6 +155,23 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
+// shared-memory byte store predicated on `loses` == 0 (one predicated STS: no divergent branch inside the placement loop)
+__device__ __forceinline__ void note_take(unsigned smem_addr, unsigned v, unsigned loses)
+{
+    asm volatile("{ .reg .pred p; setp.eq.u32 p, %2, 0; @p st.shared.u8 [%0], %1; }" ::"r"(smem_addr), "r"(v), "r"(loses) : "memory");
+}
+
+// S <- S -/+ r when `loses` == 0, as ONE predicated instruction in place (the compiler's own if-conversion computes
+// into a temporary and adds a predicated move per register half - one more dependent step on the placement chain).
+template <bool BINS>
+__device__ __forceinline__ void state_take(double &S, double r, unsigned loses)
+{
+    if (BINS)
+        asm("{ .reg .pred p; setp.eq.u32 p, %2, 0; @p sub.rn.f64 %0, %0, %1; }" : "+d"(S) : "d"(r), "r"(loses));
+    else
+        asm("{ .reg .pred p; setp.eq.u32 p, %2, 0; @p add.rn.f64 %0, %0, %1; }" : "+d"(S) : "d"(r), "r"(loses));
+}
+
 template <int D>
 __device__ __forceinline__ void load_row(double (&r)[D], const double *src)
 {
@@ -662,7 +679,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 unsigned touched_or_open = BINS ? opened[warp] : 0u;
                 unsigned touched_tile = 0u;  // nodes / bins of this warp that took a pod in this tile
 
-                unsigned ev_local = 0;
+                unsigned my_takes = 0;  // pods this lane's node / bin took in this tile
                 const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
                 unsigned head = 0;
@@ -670,7 +687,12 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 bool done = false;
                 const bool tracing = p.prof && p.trace && stage == p.trace_stage;
                 long long tw = 0, tb = 0, t_loop = 0, t_mark = tracing ? clock64() : 0;
-                unsigned n_batches = 0;
+                unsigned n_batches = 0, n_iter = 0;
+                // this lane's bit, and all bits up to it (read once from the special registers: the compiler would
+                // otherwise rematerialise shift/add sequences for them inside the loop, on the placement chain)
+                unsigned me, le;
+                asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(me));
+                asm volatile("mov.u32 %0, %%lanemask_le;" : "=r"(le));
                 while (!done) {
                     // a batch of up to 32 entries: lane i takes entry head+i with its candidate and slot;
                     // only the node state S carries a dependency from one entry to the next.
@@ -728,6 +750,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         for (int d = 0; d < D; d += 2)
                             *reinterpret_cast<double2 *>(brow + (size_t)my_rank * D + d) = make_double2(own[d], own[d + 1]);
                     }
+                    fnd[lane] = 0xFF;  // "nobody took dense entry `lane`" until a taker says otherwise
+                    const unsigned fnd_sa = (unsigned)__cvta_generic_to_shared(const_cast<unsigned char *>(fnd));
                     if (lane < 4) {
                         double *pad = brow + (size_t)(n_poss + lane) * D;
                         pad[0] = __longlong_as_double(0x7FF0000000000000ll);
@@ -738,26 +762,28 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     double r[D];
                     load_row<D>(r, brow);
                     const long long t_l0 = tracing ? clock64() : 0;
-                    unsigned took = 0;    // bit k: dense entry k of the batch was placed by this warp
-                    unsigned mymask = 0;  // bit k: ... by THIS lane's node
-                    const unsigned me = 1u << lane, le = (me << 1) - 1u;  // this lane's bit, and all bits up to it
+                    if (tracing) n_iter += (unsigned)n_poss;
                     // The placement chain.  Entry k's test needs the state left by entry k-1, which is only known once
                     // the vote of entry k-1 has named its taker.  Instead of waiting for it, both outcomes are computed
                     // while that vote is in flight: fit_keep = "entry k fits this node as it is", fit_took = "... after
                     // this node took entry k-1" (the same float64 expressions, same rounding), and the vote's answer
                     // merely selects one.  What stays on the vote-to-vote path is a predicate select and a mask
                     // compare; the float64 adds and compares run beside it.
+                    // nodes: the reference's  cap - (used + req) >= 0  (kube.py:175).  For finite float64 values the rounded
+                    // difference has the sign of the exact one and is zero only for equal operands (gradual underflow), so
+                    // fl(cap - t) >= 0  <=>  t <= cap  with t = fl(used + req): one add and one compare on the chain instead
+                    // of two adds and a compare; t is also the state the node takes on when it accepts the entry.
                     auto fits = [&](const double (&st)[D], const double (&row)[D]) {
                         bool ok = true, ok2 = true;  // two independent and-chains over the dimensions
 #pragma unroll
                         for (int d = 0; d < D / 2; ++d) {
                             if (BINS) ok = ok & (row[d] <= st[d]);   // == (st - row >= 0) for finite values (scaler.py:139)
-                            else ok = ok & (__dsub_rn(C[d], __dadd_rn(st[d], row[d])) >= 0.0);  // kube.py:175
+                            else ok = ok & (__dadd_rn(st[d], row[d]) <= C[d]);
                         }
 #pragma unroll
                         for (int d = D / 2; d < D; ++d) {
                             if (BINS) ok2 = ok2 & (row[d] <= st[d]);
-                            else ok2 = ok2 & (__dsub_rn(C[d], __dadd_rn(st[d], row[d])) >= 0.0);
+                            else ok2 = ok2 & (__dadd_rn(st[d], row[d]) <= C[d]);
                         }
                         return ok & ok2;
                     };
@@ -773,19 +799,15 @@ firstfit_pipeline_kernel(const PipelineParams p)
                             double r_next[D];
                             load_row<D>(r_next, brow + (size_t)(k + 1) * D);
                             const bool ok = fits(S, r);
-                            // two votes issued back to back: the predicate one steers the (uniform) branch without an
-                            // integer compare on the chain, the ballot names the first fitting node
-                            const bool any = __any_sync(0xFFFFFFFFu, ok);
+                            // the vote-to-vote path: ballot -> "no fitting lane before me" -> predicated update of S -> next
+                            // test.  No branch on it (at the frontier nearly every entry is taken) and no mask arithmetic
+                            // beyond one and + compare.
                             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                            if (any) {
-                                if ((m & le) == me) {  // the first fitting node of the warp takes the pod
+                            const unsigned loses = (m & le) ^ me;  // 0 <=> this is the first fitting node of the warp
 #pragma unroll
-                                    for (int d = 0; d < D; ++d)
-                                        S[d] = BINS ? __dsub_rn(S[d], r[d]) : __dadd_rn(S[d], r[d]);  // scaler.py:140 / kube.py:171
-                                    mymask |= 1u << k;
-                                }
-                                took |= 1u << k;
-                            }
+                            for (int d = 0; d < D; ++d) state_take<BINS>(S[d], r[d], loses);  // scaler.py:140 / kube.py:171
+                            note_take(fnd_sa + (unsigned)k, (unsigned)lane, loses);  // off the chain: who took entry k
+                            my_takes += loses ? 0u : 1u;
 #pragma unroll
                             for (int d = 0; d < D; ++d) r[d] = r_next[d];
                         }
@@ -813,9 +835,9 @@ firstfit_pipeline_kernel(const PipelineParams p)
                                          : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
                         fit_keep = fits(S, r_next);
                         fit_took = fits(Sm, r_next);
-                        prev_mine = (m & le) == me;  // the first fitting node of the warp takes the pod
-                        if (prev_mine) mymask |= 1u << k;
-                        if (m) took |= 1u << k;
+                        prev_mine = ((m & le) ^ me) == 0u;  // the first fitting node of the warp takes the pod
+                        note_take(fnd_sa + (unsigned)k, (unsigned)lane, prev_mine ? 0u : 1u);
+                        my_takes += prev_mine ? 1u : 0u;
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
                     }
@@ -824,23 +846,14 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         for (int d = 0; d < D; ++d) S[d] = Sm[d];
                     }
                     }  // kSpeculate
-                    for (unsigned t = mymask; t; t &= t - 1) fnd[__ffs(t) - 1] = (unsigned char)lane;
                     __syncwarp();
-                    if (took) {
-                        n_placed += __popc(took);
-                        const bool got = poss && ((took >> my_rank) & 1u);
-                        const int found = got ? (int)fnd[my_rank] : -1;
-                        placed_here = found;
-                        const unsigned acc_lanes = __reduce_or_sync(0xFFFFFFFFu, got ? (1u << found) : 0u);
-                        // credited tests (bins): every bin before the chosen one, plus the chosen one unless this
-                        // pod opened it (= the first pod ever placed in that bin); the stage/warp base is added
-                        // once per tile below
-                        ev_local += __reduce_add_sync(0xFFFFFFFFu, got ? (unsigned)found + 1u : 0u) -
-                                    (unsigned)__popc(acc_lanes & ~touched_or_open);
-                        touched_or_open |= acc_lanes;
-                        touched_tile |= acc_lanes;
+                    {
+                        const int found = poss ? (int)fnd[my_rank] : 0xFF;
+                        if (found != 0xFF) placed_here = found;
                     }
-                    if (BINS && took) {  // tighten the bound: the remaining amounts just shrank
+                    const unsigned gotmask = __ballot_sync(0xFFFFFFFFu, placed_here >= 0);
+                    n_placed += __popc(gotmask);
+                    if (BINS && gotmask) {  // tighten the bound: the remaining amounts just shrank
 #pragma unroll
                         for (int d = 0; d < D; ++d) Mx[d] = warp_upper_bound(S[d]);
                     }
@@ -862,11 +875,21 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 if (!last && lane == 0) out_q[out] = kQueueEnd;
                 if (lane == 0 && n_placed) atomicAdd(&misc[4], (unsigned)n_placed);
                 if (tracing && lane == 0 && tile < 4096 && warp < 8)
-                    p.trace[(size_t)(4096 + tile) * 8 + warp] = ((unsigned long long)(tb >> 2) & 0xFFFFF) |
-                        (((unsigned long long)(t_loop >> 2) & 0xFFFFF) << 20) | ((unsigned long long)(head & 0xFFF) << 40) |
-                        ((unsigned long long)(n_batches & 0xFF) << 52);
+                    p.trace[(size_t)(4096 + tile) * 8 + warp] = ((unsigned long long)(tb >> 5) & 0x7FFF) |
+                        (((unsigned long long)(t_loop >> 5) & 0x7FFF) << 15) | ((unsigned long long)(head & 0x1FF) << 30) |
+                        ((unsigned long long)(n_batches & 0x3F) << 39) | ((unsigned long long)(n_iter & 0x3FF) << 45) |
+                        ((unsigned long long)(n_placed & 0x1FF) << 55);
                 if (n_placed) {
-                    if (BINS) my_evals += (unsigned long long)ev_local + (unsigned long long)n_placed * (unsigned long long)(stage_lo + my_lo);
+                    // once per tile (not per batch): which lanes took a pod, and - bins - the credited tests: every bin
+                    // before the chosen one plus the chosen one unless this pod opened it (= the first pod ever placed
+                    // in that bin); the stage / warp base is added per placed pod
+                    touched_tile = __ballot_sync(0xFFFFFFFFu, my_takes != 0u);
+                    if (BINS) {
+                        const unsigned ev_local = __reduce_add_sync(0xFFFFFFFFu, my_takes * (unsigned)(lane + 1)) -
+                                                  (unsigned)__popc(touched_tile & ~touched_or_open);
+                        touched_or_open |= touched_tile;
+                        my_evals += (unsigned long long)ev_local + (unsigned long long)n_placed * (unsigned long long)(stage_lo + my_lo);
+                    }
                     if (n < Tn) {
 #pragma unroll
                         for (int d = 0; d < D; ++d) state_s[(size_t)d * Tn + n] = S[d];

@@ -29,6 +29,11 @@ def ev_time(fn, reps=3):
     return best, out
 
 
+def unpack_warp(v):
+    v = int(v)
+    return ((v & 0x7FFF) * 32, ((v >> 15) & 0x7FFF) * 32, (v >> 30) & 0x1FF, (v >> 39) & 0x3F, (v >> 45) & 0x3FF, (v >> 55) & 0x1FF)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--P", type=int, default=100000)
@@ -78,9 +83,16 @@ def main():
                 print("     tile %4d: %s | %d %d" % (t_, " ".join("%7d" % v for v in tr[t_, :6]), tr[t_, 6], tr[t_, 7]))
                 if t_ < 4096 and tr[t_, 6] > 0:
                     w = tr[4096 + t_]
-                    print("        warps (busy/wait cycles, entries, batches): " + "  ".join(
-                        "w%d %d/%d e%d b%d" % (i, (int(v) & 0xFFFFF) * 4, ((int(v) >> 20) & 0xFFFFF) * 4, (int(v) >> 40) & 0xFFF, (int(v) >> 52) & 0xFF)
-                        for i, v in enumerate(w) if v))
+                    print("        warps (batch cycles/of which loop+bookkeeping, entries seen, batches, loop iterations, placed): " + "  ".join(
+                        "w%d %d/%d e%d b%d i%d p%d" % ((i,) + unpack_warp(v)) for i, v in enumerate(w) if v))
+            ws = np.array([[unpack_warp(v) for v in tr[4096 + t_]] for t_ in act if t_ < 4096], dtype=np.int64)
+            if len(ws):
+                tot_w = ws.sum(axis=0)   # [warp, field]
+                print("   stage %d totals per warp over %d tiles (batch cycles, loop cycles, entries, batches, iterations, placed):" % (args.trace_stage, len(ws)))
+                for i in range(tot_w.shape[0]):
+                    if tot_w[i].any():
+                        print("     w%d: %s" % (i, " ".join("%8d" % v for v in tot_w[i])))
+                print("     all: iterations %d, placed %d, entries %d, resolve cycles %d" % (tot_w[:, 4].sum(), tot_w[:, 5].sum(), tr[act, 6].sum(), tr[act, 3].sum()))
         top = np.argsort(-(tot - pr[:, 0]))[:4]
         for s_ in top:
             print("   stage %4d: " % s_ + ", ".join("%s %.0fk" % (n, pr[s_, i] / 1e3) for i, n in enumerate(names))
