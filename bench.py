@@ -72,6 +72,7 @@ class ClockSampler(object):
             pynvml.nvmlInit()
             self._nvml = pynvml
             self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))  # static: read once
             self._bits = [getattr(pynvml, n, 0) for n in ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
                                                           "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
         except Exception:
@@ -81,9 +82,8 @@ class ClockSampler(object):
         if self._nvml is not None:
             n = self._nvml
             sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
-            mx = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
             mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
-            return (int(sm), int(mx), [bool(mask & b) for b in self._bits])
+            return (int(sm), self._max_mhz, [bool(mask & b) for b in self._bits])
         out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                               "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
         parts = [x.strip() for x in out.strip().split(",")]
@@ -92,6 +92,11 @@ class ClockSampler(object):
         return (int(float(parts[0])), int(float(parts[1])), [p.lower().startswith("active") for p in parts[2:6]])
 
     def _run(self):
+        # Every NVML query takes driver locks that the tick's own launches and copies need: measured on the B200 box, a
+        # 50 ms period put a 10-24 ms outlier into about one c2 step in twenty, a 1 s period none.  So: a first sample
+        # shortly after the timed region starts (the GPU is under load since the warm-up), then four per second.
+        if self._stop.wait(0.02):
+            return
         while not self._stop.is_set():
             try:
                 s = self._sample()
@@ -99,7 +104,7 @@ class ClockSampler(object):
                     self.samples.append(s)
             except Exception:
                 pass
-            self._stop.wait(0.05 if self._nvml is not None else 0.25)
+            self._stop.wait(float(os.environ.get("ACSFIT_BENCH_SAMPLE_PERIOD", 0.25)))
 
     def __enter__(self):
         self._thread.start()

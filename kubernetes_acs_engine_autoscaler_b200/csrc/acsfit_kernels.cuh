@@ -697,7 +697,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     // a batch of up to 32 entries: lane i takes entry head+i with its candidate and slot;
                     // only the node state S carries a dependency from one entry to the next.
                     const unsigned idx = head + lane <= (unsigned)kTile ? head + lane : (unsigned)kTile;
-                    unsigned e, present;
+                    unsigned e, present, endmask;
                     int nb;
                     for (unsigned spins = 0;; ++spins) {
                         e = in_q[idx];
@@ -706,27 +706,25 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         nb = __ffs(~present) ? __ffs(~present) - 1 : 32;  // written entries form a prefix
                         // a consumer warp takes entries in batches of >= kMinBatch (or up to the end marker):
                         // one-entry batches would pay the batch set-up for every pod the producer forwards
-                        const bool has_end = __any_sync(0xFFFFFFFFu, lane < nb && e == kQueueEnd);
-                        if (has_end || nb >= kMinBatch) break;
+                        endmask = __ballot_sync(0xFFFFFFFFu, lane < nb && e == kQueueEnd);
+                        if (endmask || nb >= kMinBatch) break;
                         __nanosleep(64);  // do not hammer the shared-memory pipe the producer warp needs
                         
                         if (spins > (1u << 26)) {  // never expected: refuse to hang the GPU
                             atomicExch(p.status, 2);
                             e = lane == 0 ? kQueueEnd : 0u;
                             present = 1u;
+                            endmask = 1u;
                             nb = 1;
                             break;
                         }
                     }
                     if (tracing) { const long long now = clock64(); tw += now - t_mark; t_mark = now; ++n_batches; }
-                    const unsigned endmask = __ballot_sync(0xFFFFFFFFu, lane < nb && e == kQueueEnd);
                     const int n_ent = endmask ? __ffs(endmask) - 1 : nb;
                     const bool mine = lane < n_ent;  // words after the end marker are stale: never touch them
                     const unsigned q_l = mine ? e - 1 : 0;
                     const unsigned c_l = mine ? cand[q_l] : kNoCand;
                     const unsigned s_l = mine ? slot_of[q_l] : 0;
-                    // nodes before cand[q] did not fit at tile start, hence not now either
-                    const unsigned testmask = __ballot_sync(0xFFFFFFFFu, mine && (int)c_l < my_lo + 32);
                     int placed_here = -1;  // lane i: LOCAL node (of this warp) that took entry i of the batch
                     // Which entries of the batch can this warp take at all?  Lane i checks its own entry against
                     // the per-dimension maximum over the warp's 32 nodes (an upper bound that only gets looser
@@ -738,7 +736,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     volatile unsigned char *fnd = found_s + warp * 32;
                     double own[D];
                     load_row<D>(own, rows + (size_t)q_l * D);
-                    bool poss = (testmask >> lane) & 1u;
+                    // nodes before cand[q] did not fit at tile start, hence not now either
+                    bool poss = mine && (int)c_l < my_lo + 32;
 #pragma unroll
                     for (int d = 0; d < D; ++d) poss = poss & (own[d] <= Mx[d]);
 
@@ -763,12 +762,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
                     load_row<D>(r, brow);
                     const long long t_l0 = tracing ? clock64() : 0;
                     if (tracing) n_iter += (unsigned)n_poss;
-                    // The placement chain.  Entry k's test needs the state left by entry k-1, which is only known once
-                    // the vote of entry k-1 has named its taker.  Instead of waiting for it, both outcomes are computed
-                    // while that vote is in flight: fit_keep = "entry k fits this node as it is", fit_took = "... after
-                    // this node took entry k-1" (the same float64 expressions, same rounding), and the vote's answer
-                    // merely selects one.  What stays on the vote-to-vote path is a predicate select and a mask
-                    // compare; the float64 adds and compares run beside it.
+                    // The placement chain.  Entry k's test needs the state left by entry k-1, which is only known once the
+                    // vote of entry k-1 has named its taker: the vote-to-vote path below is compare -> ballot -> mask test
+                    // -> select of the new state.  (A variant that prepared both outcomes of the next test beside the vote
+                    // was measured against this loop and dropped: it doubles the float64 work for no gain.)
                     // nodes: the reference's  cap - (used + req) >= 0  (kube.py:175).  For finite float64 values the rounded
                     // difference has the sign of the exact one and is zero only for equal operands (gradual underflow), so
                     // fl(cap - t) >= 0  <=>  t <= cap  with t = fl(used + req): one add and one compare on the chain instead
@@ -787,65 +784,24 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         }
                         return ok & ok2;
                     };
-                    // Measured (profiles/r02_summary.md): bins at D = 8 102 -> 84 ms (c3).  Not used where it loses: the D = 8
-                    // node test is 24 float64 instructions per entry and issue-bound (c3 nodes 98 -> 106 ms with it); at
-                    // D <= 4 the extra registers (122 -> 148) cost the second stage CTA per SM, and with it the
-                    // nodes -> bins chaining of the c2 tick (10.7 -> 10.9 ms; capped at 128 registers: 11.6 ms).
-                    constexpr bool kSpeculate = BINS && D >= 8;
-                    if constexpr (!kSpeculate) {
-                        for (int k0 = 0; k0 < n_poss; k0 += 4)
-#pragma unroll
-                        for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
-                            double r_next[D];
-                            load_row<D>(r_next, brow + (size_t)(k + 1) * D);
-                            const bool ok = fits(S, r);
-                            // the vote-to-vote path: ballot -> "no fitting lane before me" -> predicated update of S -> next
-                            // test.  No branch on it (at the frontier nearly every entry is taken) and no mask arithmetic
-                            // beyond one and + compare.
-                            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                            const unsigned loses = (m & le) ^ me;  // 0 <=> this is the first fitting node of the warp
-#pragma unroll
-                            for (int d = 0; d < D; ++d) state_take<BINS>(S[d], r[d], loses);  // scaler.py:140 / kube.py:171
-                            note_take(fnd_sa + (unsigned)k, (unsigned)lane, loses);  // off the chain: who took entry k
-                            my_takes += loses ? 0u : 1u;
-#pragma unroll
-                            for (int d = 0; d < D; ++d) r[d] = r_next[d];
-                        }
-                    } else {
-                    double Sm[D];  // the state this node would have after taking the previous entry
-#pragma unroll
-                    for (int d = 0; d < D; ++d) Sm[d] = S[d];
-                    bool prev_mine = false;
-                    bool fit_keep = fits(S, r), fit_took = fit_keep;
                     for (int k0 = 0; k0 < n_poss; k0 += 4)
 #pragma unroll
                     for (int k = k0; k < k0 + 4; ++k) {  // slots past n_poss hold never-fitting rows
                         double r_next[D];
                         load_row<D>(r_next, brow + (size_t)(k + 1) * D);
-                        const bool ok = prev_mine ? fit_took : fit_keep;
-                        if (prev_mine) {
-#pragma unroll
-                            for (int d = 0; d < D; ++d) S[d] = Sm[d];
-                        }
+                        const bool ok = fits(S, r);
+                        // the vote-to-vote path: ballot -> "no fitting lane before me" -> predicated update of S -> next
+                        // test.  No branch on it (at the frontier nearly every entry is taken) and no mask arithmetic
+                        // beyond one and + compare.
                         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                        // beside the vote: the state after taking THIS entry, and the next entry's test either way
+                        const unsigned loses = (m & le) ^ me;  // 0 <=> this is the first fitting node of the warp
 #pragma unroll
-                        for (int d = 0; d < D; ++d)
-                            Sm[d] = BINS ? __dsub_rn(S[d], r[d])   // bins[i] - pod.resources   scaler.py:140
-                                         : __dadd_rn(S[d], r[d]);  // used += pod.resources     kube.py:171
-                        fit_keep = fits(S, r_next);
-                        fit_took = fits(Sm, r_next);
-                        prev_mine = ((m & le) ^ me) == 0u;  // the first fitting node of the warp takes the pod
-                        note_take(fnd_sa + (unsigned)k, (unsigned)lane, prev_mine ? 0u : 1u);
-                        my_takes += prev_mine ? 1u : 0u;
+                        for (int d = 0; d < D; ++d) state_take<BINS>(S[d], r[d], loses);  // scaler.py:140 / kube.py:171
+                        note_take(fnd_sa + (unsigned)k, (unsigned)lane, loses);  // off the chain: who took entry k
+                        my_takes += loses ? 0u : 1u;
 #pragma unroll
                         for (int d = 0; d < D; ++d) r[d] = r_next[d];
                     }
-                    if (prev_mine) {  // the last entry's taker
-#pragma unroll
-                        for (int d = 0; d < D; ++d) S[d] = Sm[d];
-                    }
-                    }  // kSpeculate
                     __syncwarp();
                     {
                         const int found = poss ? (int)fnd[my_rank] : 0xFF;
@@ -938,15 +894,18 @@ firstfit_pipeline_kernel(const PipelineParams p)
         // ---- publish the surviving pods of the tile (warp 0; the others go on to the next tile) ----
         if (warp == 0) {
             forwarded += (long long)alive_total - (long long)n_placed_tile;
-            if (lane < kTile / 32 && (n_placed_tile || remote_in)) {
-                const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + lane;
-                if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[lane]);
-            }
-            __syncwarp();
             if (lane == 0) {
-                // a tile in which this stage placed nothing wrote nothing: the release alone carries the upstream
-                // stages' writes forward (release / acquire are cumulative), no fence needed
-                if (n_placed_tile || remote_in) __threadfence();
+                // ONE lane writes the tile's alive words and then the progress counter with a release store: the words
+                // precede the release in program order, so no separate fence is needed (a fence costs about as much as
+                // the release itself).  A tile in which this stage placed nothing wrote nothing: the release alone
+                // carries the upstream stages' writes forward (release / acquire are cumulative).
+                if (n_placed_tile || remote_in) {
+#pragma unroll
+                    for (int w = 0; w < kTile / 32; ++w) {
+                        const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + w;
+                        if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[w]);
+                    }
+                }
                 publish(tile + 1);
             }
         }
