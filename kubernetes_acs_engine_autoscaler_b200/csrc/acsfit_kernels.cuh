@@ -249,7 +249,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     unsigned *dirty = opened + NW;                              // [NW] nodes: threshold is stale (bit per node)
     unsigned *wcount = dirty + NW;                              // [8] pods to scan per tile word
     unsigned *acount = wcount + 8;                              // [8] alive pods per tile word
-    unsigned *misc = acount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed
+    unsigned *misc = acount + 8;                                // [8]: 0 stage, 1 abort, 2 drained, 3 any dirty, 4 placed, 5 first candidate
     unsigned *nextw = misc + 8;                                 // [kRing][8] alive words of the next tiles (ring, slot = tile % kRing)
     unsigned *hitlist = nextw + kRing * 8;                      // [kTile+1] ordered hit entries (q+1), then kQueueEnd
     unsigned *queue = hitlist + (kTile + 1);                    // [NW-1][kTile+1] forward queue of warp w -> w+1
@@ -463,7 +463,10 @@ firstfit_pipeline_kernel(const PipelineParams p)
         }
         if (tid < kTile / 32) hitmask[tid] = 0;
         if (tid < NW) dirty[tid] = 0;
-        if (tid == 0) misc[4] = 0;
+        if (tid == 0) {
+            misc[4] = 0;
+            misc[5] = 0xFFFFFFFFu;
+        }
         __syncthreads();
         unsigned base = 0, total = 0, alive_total = 0;  // total: pods to scan (compacted rows)
 #pragma unroll
@@ -628,6 +631,12 @@ firstfit_pipeline_kernel(const PipelineParams p)
             const bool hit = tid < (int)total && cand[tid] != kNoCand;
             const unsigned hw = __ballot_sync(0xFFFFFFFFu, hit);
             if (lane == 0 && warp < kTile / 32) hitmask[warp] = hw;
+            // the first candidate of the whole tile: no pod has one in a warp before it, so those warps (nodes that were
+            // full at tile start) need not pass the hit list along - the resolver chain starts at that warp
+            if (hw) {
+                const unsigned cmin = __reduce_min_sync(0xFFFFFFFFu, hit ? cand[tid] : 0xFFFFFFFFu);
+                if (lane == 0) atomicMin(&misc[5], cmin);
+            }
         }
         __syncthreads();
         ACSFIT_PROF(2)
@@ -657,7 +666,8 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (nh > 0) {
             __syncthreads();
             unsigned out = 0;
-            if (warp < n_warps) {
+            const int first_w = min((int)(misc[5] >> 5), n_warps - 1);
+            if (warp < n_warps && warp >= first_w) {
                 const int my_lo = warp << 5;
                 const int n = my_lo + lane;
                 const bool last = warp == n_warps - 1;
@@ -680,7 +690,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 unsigned touched_tile = 0u;  // nodes / bins of this warp that took a pod in this tile
 
                 unsigned my_takes = 0;  // pods this lane's node / bin took in this tile
-                const volatile unsigned *in_q = warp == 0 ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
+                const volatile unsigned *in_q = warp == first_w ? hitlist : queue + (size_t)(warp - 1) * (kTile + 1);
                 volatile unsigned *out_q = queue + (size_t)warp * (kTile + 1);
                 unsigned head = 0;
                 int n_placed = 0;
@@ -743,6 +753,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
 
                     const unsigned possmask = __ballot_sync(0xFFFFFFFFu, poss);
                     const int n_poss = __popc(possmask);
+                    if (possmask == 0u) {  // nothing this warp could take (it is full): pass the batch along and go on
+                        if (!last) {
+                            if (mine) out_q[out + lane] = e;  // the batch's entries are a prefix of the lanes
+                            out += (unsigned)n_ent;
+                        }
+                        head += (unsigned)n_ent;
+                        done = endmask != 0;
+                        if (tracing) { const long long now = clock64(); tb += now - t_mark; t_mark = now; }
+                        continue;
+                    }
                     const int my_rank = __popc(possmask & ((1u << lane) - 1u));
                     if (poss) {
 #pragma unroll
