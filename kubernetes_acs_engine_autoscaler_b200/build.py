@@ -52,5 +52,28 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def hostfast_path():
+    import sysconfig
+    return os.path.join(PKG_DIR, "_hostfast" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_hostfast(force=False):
+    """the CPython helper module of the host-side ingestion (csrc/hostfast.c; gcc, no CUDA involved).  It is an
+    accelerator only: kube.py / snapshot.py hold the same logic in Python and use it when the module is absent."""
+    import sysconfig
+    src, out = os.path.join(CSRC, "hostfast.c"), hostfast_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for _hostfast")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-Wall", "-I" + sysconfig.get_paths()["include"], "-o", out, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building _hostfast failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_hostfast(force="--force" in sys.argv))

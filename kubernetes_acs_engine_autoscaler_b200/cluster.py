@@ -14,6 +14,7 @@ import sys
 
 from . import adapters
 from . import capacity
+from . import kube
 from . import snapshot
 from . import utils
 from .deployments import Deployments
@@ -156,7 +157,7 @@ class Cluster(object):
             ignore_pools=self.ignore_pools, over_provision=self.over_provision, spare_count=self.spare_agents,
             idle_threshold=self.idle_threshold, notifier=self.notifier)
 
-        pods = list(map(KubePod, self.list_pods()))
+        pods = kube.make_pods(self.list_pods()) if KubePod is kube.KubePod else list(map(KubePod, self.list_pods()))
         running_or_pending_assigned_pods = [
             p for p in pods
             if p.status in (KubePodStatus.RUNNING, KubePodStatus.CONTAINER_CREATING)

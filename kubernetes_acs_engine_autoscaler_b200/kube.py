@@ -9,10 +9,18 @@ through to the wrapped pykube objects, exactly as the reference does (kube.py:12
 import datetime
 import json
 import logging
+import os
 
 from . import utils
 
 logger = logging.getLogger('autoscaler.kube')
+
+try:  # CPython twin of the two hottest host loops (csrc/hostfast.c); the Python code below is the definition
+    if os.environ.get('ACSFIT_NO_HOSTFAST'):
+        raise ImportError('disabled')
+    from . import _hostfast
+except ImportError:
+    _hostfast = None
 
 _CORDON_LABEL = 'openai/cordoned-by-autoscaler'
 
@@ -186,6 +194,18 @@ class KubePod(object):
         return 'KubePod({namespace}, {name})'.format(namespace=self.namespace, name=self.name)
 
     __repr__ = __str__
+
+
+_KUBEPOD_INIT = KubePod.__init__
+
+
+def make_pods(raw_pods):
+    """[KubePod(p) for p in raw_pods] (cluster.py:153 builds them with map).  With the C helper the plain pods (exact
+    dicts, memoised timestamps and requests) are built in C attribute for attribute; everything else - and every
+    pod when the helper is absent or KubePod.__init__ has been replaced - goes through the constructor."""
+    if _hostfast is None or KubePod.__init__ is not _KUBEPOD_INIT:
+        return list(map(KubePod, raw_pods))
+    return _hostfast.make_pods(KubePod, raw_pods, _TIME_MEMO, _remember_time, _RESOURCES_MEMO, _pod_resources)
 
 
 class KubeNode(object):

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .engine import Engine, padded_dims
+from .kube import _hostfast
 
 _engine = None
 
@@ -32,6 +33,22 @@ def set_engine(engine):
     return engine
 
 
+def _group(objects):
+    """(group index per object, one representative per group): identity grouping in first-occurrence order."""
+    objects = objects if isinstance(objects, list) else list(objects)
+    inv = np.empty(len(objects), dtype=np.int64)
+    if _hostfast is not None:
+        return inv, _hostfast.group_ids(objects, inv)
+    slot, uniq = {}, []
+    for i, obj in enumerate(objects):
+        j = slot.get(id(obj))
+        if j is None:
+            j = slot[id(obj)] = len(uniq)
+            uniq.append(obj)
+        inv[i] = j
+    return inv, uniq
+
+
 class Dims(object):
     """column order of one flattening.  Resource vectors are deduplicated by object identity first: pods of one
     template share their KubeResource (kube._pod_resources), so 10^5 pods flatten as a few dozen distinct rows
@@ -39,11 +56,8 @@ class Dims(object):
 
     def __init__(self, resources):
         keys = set()
-        seen = set()
-        for res in resources:
-            if id(res) not in seen:
-                seen.add(id(res))
-                keys.update(res.raw.keys())
+        for res in _group(resources)[1]:
+            keys.update(res.raw.keys())
         self.keys = sorted(keys)
         self.index = {k: i for i, k in enumerate(self.keys)}
         self.D = max(1, len(self.keys))
@@ -52,14 +66,7 @@ class Dims(object):
     def rows(self, resources, n=None):
         resources = list(resources)
         index = self.index
-        slot, uniq = {}, []
-        inv = np.empty(len(resources), dtype=np.int64)
-        for i, res in enumerate(resources):
-            j = slot.get(id(res))
-            if j is None:
-                j = slot[id(res)] = len(uniq)
-                uniq.append(res)
-            inv[i] = j
+        inv, uniq = _group(resources)
         urows = np.zeros((len(uniq), self.Dp), dtype=np.float64)
         for j, res in enumerate(uniq):
             for key, value in res.raw.items():
