@@ -887,6 +887,26 @@ firstfit_pipeline_kernel(const PipelineParams p)
         if (p.prof && tid == 0) { prof_acc[6] += nh; prof_acc[7] += 1; }
         const unsigned n_placed_tile = nh ? misc[4] : 0u;
 
+        // ---- publish the surviving pods of the tile FIRST (warp 0): the next stage can start on the tile while this one
+        // refreshes its own thresholds (the refresh only concerns this stage's later tiles) ----
+        if (warp == 0) {
+            forwarded += (long long)alive_total - (long long)n_placed_tile;
+            if (lane == 0) {
+                // ONE lane writes the tile's alive words and then the progress counter with a release store: the words
+                // precede the release in program order, so no separate fence is needed (a fence costs about as much as
+                // the release itself).  A tile in which this stage placed nothing wrote nothing: the release alone
+                // carries the upstream stages' writes forward (release / acquire are cumulative).
+                if (n_placed_tile || remote_in) {
+#pragma unroll
+                    for (int w = 0; w < kTile / 32; ++w) {
+                        const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + w;
+                        if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[w]);
+                    }
+                }
+                publish(tile + 1);
+            }
+        }
+        ACSFIT_PROF(4)
         // ---- nodes: refresh the scan thresholds of the nodes that took a pod (all threads) ----
         if ((!BINS || RW > 0) && n_placed_tile) {
             if constexpr (RW > 0) {  // the packed rows of the nodes that took a pod are rebuilt field by field
@@ -910,26 +930,6 @@ firstfit_pipeline_kernel(const PipelineParams p)
             refresh_bounds();
         }
         ACSFIT_PROF(5)
-
-        // ---- publish the surviving pods of the tile (warp 0; the others go on to the next tile) ----
-        if (warp == 0) {
-            forwarded += (long long)alive_total - (long long)n_placed_tile;
-            if (lane == 0) {
-                // ONE lane writes the tile's alive words and then the progress counter with a release store: the words
-                // precede the release in program order, so no separate fence is needed (a fence costs about as much as
-                // the release itself).  A tile in which this stage placed nothing wrote nothing: the release alone
-                // carries the upstream stages' writes forward (release / acquire are cumulative).
-                if (n_placed_tile || remote_in) {
-#pragma unroll
-                    for (int w = 0; w < kTile / 32; ++w) {
-                        const int64_t wj = (int64_t)(p.tile_lo + tile) * (kTile / 32) + w;
-                        if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[w]);
-                    }
-                }
-                publish(tile + 1);
-            }
-        }
-        ACSFIT_PROF(4)
         if (p.prof && p.trace && tid == 0 && stage == p.trace_stage) {
             for (int i = 0; i < 6; ++i) {
                 p.trace[(size_t)tile * 8 + i] = prof_acc[i] - trace_prev[i];
