@@ -540,7 +540,7 @@ def run_single(args):
     peak, peak_src = load_peaks()
     with ClockSampler(0) as clocks:
         res, dev_ms, launches = timed(w.step_device, args.steps, args.warmup, flush, nb, lambda: eng.launch_count)
-        step_ms = sorted(LAST_STEP_MS)
+        step_ms, steps_in_order = sorted(LAST_STEP_MS), [round(x, 3) for x in LAST_STEP_MS]
         res_h, host_ms, _ = timed(w.step_host, args.steps, max(1, args.warmup // 2), flush, nb, lambda: eng.launch_count)
     assert res_h["decisions"] == res["decisions"]
     k_ms, k_dec, k_bytes = w.pipeline_leg(flush, max(1, min(args.steps, 5)))
@@ -554,6 +554,7 @@ def run_single(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "ms_per_step_spread": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
+        "ms_steps": steps_in_order,  # every timed step, in order (value / ms_per_step are their mean)
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, P, N, D, T, 1), "seed": SEED,

@@ -39,10 +39,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, profile=False):
+    """profile=True (or $ACSFIT_PROFILE=1) compiles the per-stage clock64 probe of tools/perf_probe.py into the
+    pipeline kernel; the default build leaves it out (its accumulators cost registers in the placement loop)."""
+    profile = profile or os.environ.get("ACSFIT_PROFILE") == "1"
+    if not force and not profile and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DACSFIT_PROFILE=1"] if profile else []) + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -75,5 +78,5 @@ def build_hostfast(force=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))
     print(build_hostfast(force="--force" in sys.argv))

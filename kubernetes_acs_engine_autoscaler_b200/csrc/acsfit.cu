@@ -847,6 +847,8 @@ extern "C" ACSFIT_API acsfit_status acsfit_debug_profile(acsfit_ctx *ctx, int en
                                                          int max_stages, int *out_stages)
 {
     if (!ctx) return ACSFIT_E_INVALID;
+    if (enabled && !kProfileBuild)
+        return fail(ctx, ACSFIT_E_INVALID, "the stage profile is compiled out: rebuild with `python -m kubernetes_acs_engine_autoscaler_b200.build --profile`");
     if (enabled && !ctx->prof_dev) {
         CUDA_TRY(cudaMalloc(&ctx->prof_dev, sizeof(unsigned long long) * (kProfStages + kProfTiles) * 8));
     }
@@ -1045,6 +1047,7 @@ static acsfit_status launch_stream(acsfit_ctx *ctx, const PipelineParams &pp, in
     return ACSFIT_OK;
 }
 
+constexpr int kOneCtaSmemKb = 116;  // more than half of the 227 KB an SM offers: a second CTA cannot be resident
 template <int D, bool BINS, bool PRUNE, int RW>
 static acsfit_status launch_pipeline_w(acsfit_ctx *ctx, const PipelineParams &pp, int stages, cudaStream_t st, int *resident)
 {
@@ -1053,6 +1056,10 @@ static acsfit_status launch_pipeline_w(acsfit_ctx *ctx, const PipelineParams &pp
     }
     constexpr int NT = stage_threads(D, BINS);
     size_t smem = PipelineSmem<D, BINS, NT, PRUNE, RW>::bytes(pp.Tn);
+    // D >= 8: ONE stage CTA per SM.  Whether two fit is an accident of the register allocation (the bins kernel has
+    // been compiled to 128 and to 237 registers by neighbouring source revisions); measured at c3, a second CTA on the
+    // frontier's SM costs the placement chain more than the extra resident stages give back (bins 89 -> 76 ms).
+    if (D >= 8) smem = std::max(smem, (size_t)kOneCtaSmemKb * 1024);
     if (ctx->smem_floor_kb > 0) smem = std::max(smem, (size_t)ctx->smem_floor_kb * 1024);  // occupancy knob
     auto kern = firstfit_pipeline_kernel<D, BINS, NT, PRUNE, RW>;
     if (resident) {  // only asked: how many stages does the GPU hold at once?  (cached: the query costs ~10 us)
@@ -1069,6 +1076,11 @@ static acsfit_status launch_pipeline_w(acsfit_ctx *ctx, const PipelineParams &pp
     }
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PipelineParams q = pp;
+    {   // more stages than the GPU holds at once: several waves, each streaming the whole pod list (see the kernel's publish)
+        int held = 0;
+        TRY((launch_pipeline_w<D, BINS, PRUNE, RW>(ctx, pp, stages, st, &held)));
+        q.publish_every = (held > 0 && stages > held) ? kPublishEvery : 1;
+    }
     q.prof = (ctx->prof_dev && stages <= kProfStages) ? ctx->prof_dev : nullptr;
     if (q.prof) {
         CUDA_TRY(cudaMemsetAsync(ctx->prof_dev, 0, sizeof(unsigned long long) * (kProfStages + kProfTiles) * 8, st));

@@ -43,6 +43,12 @@ __host__ __device__ constexpr int nodes_per_thread(int D, int NW = 0)
 }
 constexpr unsigned kNoCand = 0xFFFFFFFFu;
 constexpr unsigned kQueueEnd = 0xFFFFFFFFu;
+#ifndef ACSFIT_PROFILE
+#define ACSFIT_PROFILE 0
+#endif
+constexpr bool kProfileBuild = ACSFIT_PROFILE != 0;
+constexpr int kPublishEvery = 4;  // multi-wave passes: tiles between two progress publications of a stage that is not placing
+constexpr int kPublishGrace = 8;  // ... once it has not placed anything for this many tiles
 constexpr int kMinBatch = 4;  // entries a consumer warp waits for before it starts a batch
 constexpr int kMaxDims = 16;
 constexpr int kRing = 8;      // tiles whose alive words a stage fetches in one go once its upstream is that far ahead
@@ -111,6 +117,7 @@ struct PipelineParams {
     const uint32_t *alive_in; // optional: stage 0 reads the tile's alive words HERE (the upstream pipeline's
                             // bitmap in a peer GPU's memory) and always writes them to `alive`
     int sys_scope;          // cluster mode: upstream poll and the last stage's publish use system scope
+    int publish_every;      // progress of a stage that is not placing is published every this many tiles (>= 1)
     int tile_lo;            // first tile of this launch in the pod list (pod blocks); tiles are numbered
                             // locally in the progress counters, globally in alive / placed / pod_idx
     RankLayout rk;          // packed-rank scan tables (rk.nw == NW of the instantiation)
@@ -227,8 +234,10 @@ __device__ __forceinline__ unsigned wait_entry(const volatile unsigned *slot, in
     return e;
 }
 
+// D <= 4: two stage CTAs per SM are part of the design (the node and the bin launch of a tick run chained, both resident),
+// so the register budget is pinned to 128 instead of being left to the allocator's mood; D >= 8 runs one CTA per SM.
 template <int D, bool BINS, int NT, bool PRUNE, int RW>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, D <= 4 ? 2 : 1)
 firstfit_pipeline_kernel(const PipelineParams p)
 {
     constexpr int K = nodes_per_thread(D, RW);  // RW: 32-bit words of a packed-rank row, 0 = float64 scan
@@ -358,11 +367,15 @@ firstfit_pipeline_kernel(const PipelineParams p)
     const int PG = NT / NS;
     unsigned long long my_evals = 0;
     long long forwarded = 0;  // (warp 0) pods this stage passed on to the next one
+    int since_placed = 1 << 20;  // (thread 0) tiles since this stage last placed a pod
+    // developer probe (tools/perf_probe.py): compiled in only with -DACSFIT_PROFILE=1 (python -m ...build --profile); the
+    // accumulators and clock reads cost registers the placement loop wants
+    const bool PROF_ON = kProfileBuild && p.prof != nullptr;
     unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (thread 0) wait/load/scan/resolve/publish/refresh/hits/tiles
     unsigned long long trace_prev[6] = {0, 0, 0, 0, 0, 0};
     long long tp = 0;
 #define ACSFIT_PROF(i)                                   \
-    if (p.prof && tid == 0) {                            \
+    if (PROF_ON && tid == 0) {                            \
         const long long now__ = clock64();               \
         prof_acc[i] += (unsigned long long)(now__ - tp); \
         tp = now__;                                      \
@@ -395,7 +408,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     int known = 0, ring_hi = 0;  // (warp 1) tiles the upstream is known to have published / whose alive words are in the ring
 
     for (int tile = 0; tile < p.num_tiles; ++tile) {
-        if (p.prof && tid == 0) tp = clock64();
+        if (PROF_ON && tid == 0) tp = clock64();
         // ---- wait until the previous stage has published this tile (warp 1 polls, so that warp 0
         //      can still be publishing the previous tile) ---------------------------------------
         //      The same warp then fetches the tile's alive words, so that their L2 (or NVLink) latency is
@@ -695,7 +708,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
                 unsigned head = 0;
                 int n_placed = 0;
                 bool done = false;
-                const bool tracing = p.prof && p.trace && stage == p.trace_stage;
+                const bool tracing = PROF_ON && p.trace && stage == p.trace_stage;
                 long long tw = 0, tb = 0, t_loop = 0, t_mark = tracing ? clock64() : 0;
                 unsigned n_batches = 0, n_iter = 0;
                 // this lane's bit, and all bits up to it (read once from the special registers: the compiler would
@@ -884,7 +897,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
             }
         }
         ACSFIT_PROF(3)
-        if (p.prof && tid == 0) { prof_acc[6] += nh; prof_acc[7] += 1; }
+        if (PROF_ON && tid == 0) { prof_acc[6] += nh; prof_acc[7] += 1; }
         const unsigned n_placed_tile = nh ? misc[4] : 0u;
 
         // ---- publish the surviving pods of the tile FIRST (warp 0): the next stage can start on the tile while this one
@@ -903,7 +916,16 @@ firstfit_pipeline_kernel(const PipelineParams p)
                         if (wj * 32 < p.M) __stcg(p.alive + wj, alive_w[w]);
                     }
                 }
-                publish(tile + 1);
+                // A tile this stage placed nothing in changes nothing downstream needs at once.  In a pass of several
+                // waves of stage CTAs (throughput-bound: every wave streams the whole pod list) its progress is published
+                // with the next placing tile, every p.publish_every-th tile or the last one, whichever comes first - a
+                // release store costs > 1000 cycles, as much as the rest of such a tile (c4 node pass 2.97 -> 2.63 s).
+                // The frontier, which places, and the stages it has just left publish every tile; so does every stage of
+                // a single-wave pass (latency-bound: publish_every = 1; batching cost the c2 tick 2 %).
+                since_placed = n_placed_tile ? 0 : since_placed + 1;
+                if (since_placed < kPublishGrace || remote_in || sys_out || ((tile + 1) % p.publish_every) == 0 ||
+                    tile + 1 == p.num_tiles)
+                    publish(tile + 1);
             }
         }
         ACSFIT_PROF(4)
@@ -930,7 +952,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
             refresh_bounds();
         }
         ACSFIT_PROF(5)
-        if (p.prof && p.trace && tid == 0 && stage == p.trace_stage) {
+        if (PROF_ON && p.trace && tid == 0 && stage == p.trace_stage) {
             for (int i = 0; i < 6; ++i) {
                 p.trace[(size_t)tile * 8 + i] = prof_acc[i] - trace_prev[i];
                 trace_prev[i] = prof_acc[i];
@@ -952,7 +974,7 @@ firstfit_pipeline_kernel(const PipelineParams p)
     if (tid == 0) {
         if (misc[2]) publish(p.num_tiles);
         if (forwarded == 0) atomicExch(p.drained, 1);
-        if (p.prof) {
+        if (PROF_ON) {
             for (int i = 0; i < 8; ++i) p.prof[(size_t)stage * 8 + i] = prof_acc[i];
         }
     }

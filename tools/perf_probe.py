@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""developer probe: per-phase device timings of the tick at a given shape (not a bench value)."""
+"""developer probe: per-phase device timings of the tick at a given shape (not a bench value).
+--prof needs a library built with the stage profile: python -m kubernetes_acs_engine_autoscaler_b200.build --force --profile
+(rebuild without --profile afterwards: the probe costs registers in the placement loop)."""
 import argparse
 import os
 import sys
