@@ -362,16 +362,27 @@ def timed(step_fn, steps, warmup, flush, barrier, launch_count):
     for _ in range(warmup):
         step_fn()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    barrier()
-    l0 = launch_count()
-    res = None
-    for a, b in ev:
-        flush.fill_(1)  # evict L2 between timed iterations
-        torch.cuda.synchronize()
-        a.record()
-        res = step_fn()
-        b.record()
-    barrier()
+    # CPython's cyclic GC is paused over the timed steps (as Cluster.loop_logic pauses it over a tick): a generation-2
+    # pass over the interpreter's ~10^6 objects (torch is imported) takes 10-30 ms and lands inside some step, between two
+    # launches of the tick - measured as one c3 step in eight at 187 instead of 154 ms.
+    import gc
+    gc.collect()
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        barrier()
+        l0 = launch_count()
+        res = None
+        for a, b in ev:
+            flush.fill_(1)  # evict L2 between timed iterations
+            torch.cuda.synchronize()
+            a.record()
+            res = step_fn()
+            b.record()
+        barrier()
+    finally:
+        if gc_was_on:
+            gc.enable()
     global LAST_STEP_MS
     LAST_STEP_MS = [a.elapsed_time(b) for a, b in ev]
     return res, sum(LAST_STEP_MS), launch_count() - l0
@@ -561,7 +572,8 @@ def run_single(args):
                    "decisions_per_step": int(res["decisions"]), "pods_to_schedule": res["n_to_schedule"],
                    "pending": res["n_pending"], "bins_opened": [int(x) for x in res["bins_opened"]],
                    "tick": "occupancy (K1) + scale_up (K0, nodes pass, bin passes) + node_states (K6) + maintain",
-                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "1 rank"},
+                   "l2": "flushed between timed iterations (256 MiB fill)", "python_gc": "paused over the timed steps",
+                   "parallelism": "1 rank"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("pipeline_%s" % args.config), "peak_source": peak_src,
                      "kernel": "firstfit_pipeline_kernel (nodes + bins launches)", "kernel_ms_per_step": k_ms,
@@ -725,6 +737,7 @@ def run_cluster(args):
         "config": {"workload": head["workload"], "seed": SEED, "decisions_per_step": head["decisions_per_step"],
                    "pods_to_schedule": head["pods_to_schedule"], "pending": head["pending"],
                    "bins_opened": head["bins_opened"], "l2": "flushed between timed iterations (256 MiB fill)",
+                   "python_gc": "paused over the timed steps",
                    "tick": "occupancy (K1, replicated) + scale_up in cluster mode (node / bin axis split over the ranks, "
                            "stage pipeline continued over NVLink peer memory) + NCCL all-reduce of the per-pool counts "
                            "+ node_states (K6) + maintain (replicated)",
