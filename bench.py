@@ -401,8 +401,8 @@ def physical_roofline(kernel_dec_per_s, nw, sm_mhz, kernel_ms=None, placements=N
     out = {"achieved": kernel_dec_per_s, "unit": UNIT}
     if nw:
         ops = 2 * nw + 1
-        out["limiter"] = ("the sequential placement chain (see chain_ns_per_placement; a placing step costs ~110-260 cycles "
-                          "on the frontier warp and nothing else can proceed past it); the scan's own ceiling is int32 "
+        out["limiter"] = ("the sequential placement chain (see chain_ns_per_placement; a placing step costs ~77 cycles in the "
+                          "frontier warp's loop plus per-batch and per-tile work, and nothing else can proceed past it); the scan's own ceiling is int32 "
                           "issue: %d ops per pair at %d packed word(s) per row" % (ops, nw))
         out["ceiling"] = sms * INT_LANE_OPS_PER_CLK_SM * sm_mhz * 1e6 / ops
         out["frac"] = kernel_dec_per_s / out["ceiling"]
