@@ -212,10 +212,11 @@ class Cluster(object):
         pending_unassigned_pods = [p for p in pods if p.status == KubePodStatus.PENDING and (not p.node_name)]
         feasible = snapshot.feasible_pods(pending_unassigned_pods, agent_pools)
         pods_to_schedule = []
+        warn = logger.isEnabledFor(logging.WARNING)  # (the message is formatted eagerly, as upstream: skip it when nobody listens)
         for pod, ok in zip(pending_unassigned_pods, feasible):
             if ok:
                 pods_to_schedule.append(pod)
-            else:
+            elif warn:
                 logger.warning("Pending pod %s cannot fit. "
                             "Please check that requested resource amount is "
                             "consistent with node size."

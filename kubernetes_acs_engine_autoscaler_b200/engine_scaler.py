@@ -112,10 +112,13 @@ class EngineScaler(Scaler):
             state_dev = snapshot.node_states(nodes, lists, bool(pods_to_schedule), self.idle_threshold)
             states, actions = snapshot.maintain_actions(state_dev, node_pool, budget0, [1] * len(budget0),
                                                         self.dry_run)
+            info = logger.isEnabledFor(logging.INFO)  # (formatted eagerly, as upstream: skipped when nobody listens)
+            states, actions = states.tolist(), actions.tolist()
             for i, node in enumerate(nodes):
-                state = STATE_NAMES[int(states[i])]
-                logger.info("node: %-*s state: %s" % (75, node, state))
-                action = int(actions[i])
+                state = STATE_NAMES[states[i]]
+                if info:
+                    logger.info("node: %-*s state: %s" % (75, node, state))
+                action = actions[i]
                 if action == ACT_NONE:
                     if state not in (ClusterNodeState.POD_PENDING, ClusterNodeState.BUSY,
                                      ClusterNodeState.SPARE_AGENT, ClusterNodeState.GRACE_PERIOD,

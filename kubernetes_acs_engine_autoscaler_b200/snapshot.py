@@ -63,7 +63,8 @@ class Dims(object):
         self.D = max(1, len(self.keys))
         self.Dp = padded_dims(self.D)
 
-    def rows(self, resources, n=None):
+    def rows(self, resources, n=None, groups=False):
+        """[len(resources), Dp] float64 rows; with groups=True also (group index per row, the distinct vectors)."""
         resources = list(resources)
         index = self.index
         inv, uniq = _group(resources)
@@ -74,7 +75,26 @@ class Dims(object):
         out = np.zeros((len(resources) if n is None else n, self.Dp), dtype=np.float64)
         if len(resources):
             out[:len(resources)] = urows[inv]
-        return out
+        return (out, inv, uniq) if groups else out
+
+
+def _touched_keys(node_of, inv, uniq):
+    """{node: union of the key sets of the vectors counted on it}: one set update per distinct (node, vector) pair
+    instead of one per pod (the pods of a template share their vector)."""
+    touched = {}
+    if not len(node_of):
+        return touched
+    G = max(1, len(uniq))
+    pairs = np.unique(np.asarray(node_of, dtype=np.int64) * G + np.asarray(inv, dtype=np.int64))
+    keysets = [set(u.raw) for u in uniq]
+    for pair in pairs.tolist():
+        n, g = divmod(pair, G)
+        have = touched.get(n)
+        if have is None:
+            touched[n] = set(keysets[g])
+        else:
+            have.update(keysets[g])
+    return touched
 
 
 def _check_finite(a, what):
@@ -164,7 +184,7 @@ def count_running_pods(nodes, running_pods):
     if not len(run_idx):
         return
     dims = Dims([p.resources for p in running_pods] + [n.used_capacity for n in nodes])
-    req_run = dims.rows(running_pods[j].resources for j in run_idx)  # rows in node order: a contiguous table
+    req_run, inv_run, uniq_run = dims.rows((running_pods[j].resources for j in run_idx), groups=True)  # rows in node order: a contiguous table
     if (req_run < 0).any() or np.isnan(req_run).any():
         raise ValueError("negative or NaN resource request")
     used = dims.rows(n.used_capacity for n in nodes)
@@ -172,15 +192,8 @@ def count_running_pods(nodes, running_pods):
     d_used = eng.dev(used, torch.float64)
     eng.occupancy(eng.dev(row_ptr, torch.int64), None, eng.dev(req_run, torch.float64), d_used)
     used = d_used.cpu().numpy()
-    touched = {}
-    for n in range(len(nodes)):
-        lo, hi = row_ptr[n], row_ptr[n + 1]
-        if hi > lo:
-            keys = set()
-            for j in run_idx[lo:hi]:
-                keys.update(running_pods[j].resources.raw)
-            touched[n] = keys
-    _write_back_used(nodes, dims, used, touched)
+    node_of_row = np.repeat(np.arange(len(nodes), dtype=np.int64), np.diff(row_ptr))
+    _write_back_used(nodes, dims, used, _touched_keys(node_of_row, inv_run, uniq_run))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,7 +206,7 @@ def first_fit_nodes(pods, nodes):
     if not pods or not nodes:
         return placed
     dims = Dims([p.resources for p in pods] + [n.capacity for n in nodes] + [n.used_capacity for n in nodes])
-    req = dims.rows(p.resources for p in pods)
+    req, inv_req, uniq_req = dims.rows((p.resources for p in pods), groups=True)
     bad = _nonfinite_rows(req)  # infinite request: can_fit is False on every node
     ok_idx = np.nonzero(~bad)[0].astype(np.int32)
     cap, node_type = _node_types(nodes, dims)
@@ -210,10 +223,8 @@ def first_fit_nodes(pods, nodes):
     else:
         placed = res
     used = d_used.cpu().numpy()
-    touched = {}
-    for i in np.nonzero(placed >= 0)[0]:
-        touched.setdefault(int(placed[i]), set()).update(pods[i].resources.raw)
-    _write_back_used(nodes, dims, used, touched)
+    sel = np.nonzero(placed >= 0)[0]
+    _write_back_used(nodes, dims, used, _touched_keys(placed[sel], inv_req[sel], uniq_req))
     return placed
 
 
@@ -296,10 +307,17 @@ def pod_flags(pod, now_by_tz=None):
     return flags
 
 
-def node_age_seconds(node):
-    """(now - creation).seconds -- wraps at one day, like the reference (scaler.py:78)."""
+def node_age_seconds(node, now_by_tz=None):
+    """(now - creation).seconds -- wraps at one day, like the reference (scaler.py:78).  `now_by_tz`: one clock
+    reading per time zone and batch, as in pod_flags (now(tz) on a dateutil zone costs ~10 us: it converts from UTC)."""
     from . import utils
-    return (utils.now(node.creation_time.tzinfo) - node.creation_time).seconds
+    tz = node.creation_time.tzinfo
+    if now_by_tz is None:
+        return (utils.now(tz) - node.creation_time).seconds
+    now = now_by_tz.get(id(tz))
+    if now is None:
+        now = now_by_tz[id(tz)] = utils.now(tz)
+    return (now - node.creation_time).seconds
 
 
 def node_states(nodes, pods_lists, any_pending, idle_threshold):
@@ -319,7 +337,7 @@ def node_states(nodes, pods_lists, any_pending, idle_threshold):
     flags = np.asarray([pod_flags(p, clock) for p in flat], dtype=np.uint8)
     cap, node_type = _node_types(nodes, dims)
     node_flags = np.asarray([NODE_UNSCHEDULABLE if n.unschedulable else 0 for n in nodes], dtype=np.uint8)
-    age = np.asarray([node_age_seconds(n) for n in nodes], dtype=np.int64)
+    age = np.asarray([node_age_seconds(n, clock) for n in nodes], dtype=np.int64)
     eng = get_engine()
     st = eng.node_states(eng.dev(row_ptr, torch.int64),
                          None,  # contiguous table: the rows ARE in node order (bulk-copy streaming kernel)
