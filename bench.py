@@ -77,6 +77,10 @@ class ClockSampler(object):
                                                           "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
         except Exception:
             self._nvml = None
+        try:  # one throw-away reading now: the first query of a process initialises driver paths (measured: a 7.7 ms
+            self._sample()  # stall of the concurrently running tick when it happened inside the timed region)
+        except Exception:
+            pass
 
     def _sample(self):
         if self._nvml is not None:
