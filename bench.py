@@ -85,9 +85,8 @@ class ClockSampler(object):
     def _sample(self):
         if self._nvml is not None:
             n = self._nvml
-            what = os.environ.get("ACSFIT_BENCH_SAMPLE_WHAT", "both")  # developer switch (which query perturbs the run)
-            sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM) if what != "reasons" else 0
-            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle) if what != "clock" else 0
+            sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
             return (int(sm), self._max_mhz, [bool(mask & b) for b in self._bits])
         out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                               "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
