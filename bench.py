@@ -360,10 +360,20 @@ class Workload(object):
 LAST_STEP_MS = []
 
 
-def timed(step_fn, steps, warmup, flush, barrier, launch_count):
+MIN_WARM_SECONDS = 0.25
+
+
+def timed(step_fn, steps, warmup, flush, barrier, launch_count, min_warm_seconds=0.0):
     import torch
-    for _ in range(warmup):
+    # W untimed steps, and (single-process runs: min_warm_seconds > 0) at least that long: the per-step list of the
+    # round-2 runs shows the first one or two timed steps slower than the rest (8.9-9.0 against 8.7 ms, once 16 ms)
+    # when the SM clock is still ramping up from idle after only ~30 ms of load.  (Never time-based under torchrun:
+    # cluster-mode ticks are collective, every rank must run the same number of them.)
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < warmup or (warmup > 0 and time.perf_counter() - t_warm < min_warm_seconds):
         step_fn()
+        n_warm += 1
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     # CPython's cyclic GC is paused over the timed steps (as Cluster.loop_logic pauses it over a tick): a generation-2
     # pass over the interpreter's ~10^6 objects (torch is imported) takes 10-30 ms and lands inside some step, between two
@@ -424,8 +434,8 @@ def sub_record_c3(eng, syn, flush, steps, peak):
     c = syn.make_cluster(P, N, D, T, seed=SEED)
     w = Workload(eng, c)
     nb = lambda: torch.cuda.synchronize()  # noqa: E731
-    res, dev_ms, _ = timed(w.step_device, steps, 2, flush, nb, lambda: eng.launch_count)
-    res_h, host_ms, _ = timed(w.step_host, steps, 1, flush, nb, lambda: eng.launch_count)
+    res, dev_ms, _ = timed(w.step_device, steps, 2, flush, nb, lambda: eng.launch_count, MIN_WARM_SECONDS)
+    res_h, host_ms, _ = timed(w.step_host, steps, 1, flush, nb, lambda: eng.launch_count, MIN_WARM_SECONDS)
     assert res_h["decisions"] == res["decisions"]
     k_ms, k_dec, k_bytes = w.pipeline_leg(flush, min(steps, 3))
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
@@ -553,9 +563,9 @@ def run_single(args):
     nb = lambda: torch.cuda.synchronize()  # noqa: E731
     peak, peak_src = load_peaks()
     with ClockSampler(0) as clocks:
-        res, dev_ms, launches = timed(w.step_device, args.steps, args.warmup, flush, nb, lambda: eng.launch_count)
+        res, dev_ms, launches = timed(w.step_device, args.steps, args.warmup, flush, nb, lambda: eng.launch_count, MIN_WARM_SECONDS)
         step_ms, steps_in_order = sorted(LAST_STEP_MS), [round(x, 3) for x in LAST_STEP_MS]
-        res_h, host_ms, _ = timed(w.step_host, args.steps, max(1, args.warmup // 2), flush, nb, lambda: eng.launch_count)
+        res_h, host_ms, _ = timed(w.step_host, args.steps, max(1, args.warmup // 2), flush, nb, lambda: eng.launch_count, MIN_WARM_SECONDS)
     assert res_h["decisions"] == res["decisions"]
     k_ms, k_dec, k_bytes = w.pipeline_leg(flush, max(1, min(args.steps, 5)))
     stats = eng.pipeline_stats()
@@ -576,6 +586,7 @@ def run_single(args):
                    "pending": res["n_pending"], "bins_opened": [int(x) for x in res["bins_opened"]],
                    "tick": "occupancy (K1) + scale_up (K0, nodes pass, bin passes) + node_states (K6) + maintain",
                    "l2": "flushed between timed iterations (256 MiB fill)", "python_gc": "paused over the timed steps",
+                   "warm_up": "W untimed steps, continued until %.2f s have passed (SM clock settled)" % MIN_WARM_SECONDS,
                    "parallelism": "1 rank"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("pipeline_%s" % args.config), "peak_source": peak_src,
