@@ -37,15 +37,16 @@ class Lines(logging.Handler):
         self.lines.append(record.getMessage())
 
 
-@pytest.mark.parametrize("P,N,T,seed,max_size", [(1500, 200, 2, 901, None), (900, 120, 1, 902, None), (1200, 150, 2, 903, 40)])
-def test_loop_logic_equals_the_live_reference(oracle_mod, tmp_path, monkeypatch, P, N, T, seed, max_size):
+@pytest.mark.parametrize("P,N,D,T,seed,max_size", [(1500, 200, 4, 2, 901, None), (900, 120, 4, 1, 902, None),
+                                                     (1200, 150, 4, 2, 903, 40), (1200, 160, 8, 8, 904, None)])
+def test_loop_logic_equals_the_live_reference(oracle_mod, tmp_path, monkeypatch, P, N, D, T, seed, max_size):
     import ref_bench
     from oracle_engine import OracleEngine
-    from kubernetes_acs_engine_autoscaler_b200 import agent_pool, engine_scaler, snapshot, utils
+    from kubernetes_acs_engine_autoscaler_b200 import agent_pool, capacity, engine_scaler, snapshot, utils
     from kubernetes_acs_engine_autoscaler_b200 import synthetic as syn
     from kubernetes_acs_engine_autoscaler_b200.cluster import Cluster
 
-    c = syn.make_cluster(P, N, 4, T, seed=seed, over_provision=1)
+    c = syn.make_cluster(P, N, D, T, seed=seed, over_provision=1)
     cap = int(max_size if max_size is not None else c["pool_max"][0])
 
     # ---- the reference, live -------------------------------------------------------------------
@@ -79,6 +80,7 @@ def test_loop_logic_equals_the_live_reference(oracle_mod, tmp_path, monkeypatch,
     monkeypatch.setattr(utils, "now", lambda tz=None: syn.NOW if tz is None else syn.NOW.astimezone(tz))
     prev = snapshot._engine
     snapshot.set_engine(OracleEngine())
+    capacity.load(ref_bench.capacity_file(c, str(tmp_path)))  # the table the reference run above was given (D = 8: generated)
     handler = Lines()
     log = logging.getLogger("autoscaler")
     log.addHandler(handler)
@@ -94,6 +96,7 @@ def test_loop_logic_equals_the_live_reference(oracle_mod, tmp_path, monkeypatch,
         log.removeHandler(handler)
         log.setLevel(old_level)
         snapshot._engine = prev
+        capacity.load()
 
     # ---- compare ---------------------------------------------------------------------------------
     assert (exc is None) == (ref["exception"] is None)
